@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py - trajectory-steps/s of the fp64 Wagner-Platen hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of BASELINE config C2: the drifted 2-D polar random walk with
+non-commutative noise (reference examples/examples_from_paper/polar_random_walk.py:8-20),
+Wagner-Platen, fp64, p=10, 10^7 trajectories per GPU, the strong/weak-order sweep
+dt = 2^-1 ... 2^-9 (9 launches, 1022 steps per trajectory), final states + error moments.
+
+* value      device-timed (CUDA events, max over ranks) whole-job trajectory-steps/s, x0 resident in HBM.
+* e2e        the same sweep through SDESolver.solve_many with host buffers: x0 from pinned host
+             memory every launch and the final time/state/Wiener arrays copied back to the host.
+* roofline   algorithmic flops (10.9 kflop per C2 Wagner-Platen trajectory-step)
+             / kernel time, against the FP64 FMA peak measured in this run.
+* cpu_baseline / --impl reference: the numpy/torch CPU port of the reference (oracle/) on a bounded
+             sample of the same workload (JAX, hence the reference itself, is not installable here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "trajectory-steps/sec fp64 Wagner-Platen"
+UNIT = "trajectory-steps/s"
+DT_EXPONENTS = list(range(1, 10))
+N_TRAJ_PER_GPU = 10 ** 7
+TMAX = 1.0
+Y_DRIFT = 4.0
+FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10)
+THEORETICAL_MEAN_PHI = 1.10714532096375
+
+
+def workload_config(n_traj, n_gpus):
+    return {"workload": "C2 drifted polar random walk (d=m=2, non-commutative noise), wagner_platen p=10, "
+                        "strong/weak order sweep dt=2^-1..2^-9, T=1",
+            "n_trajectories_per_gpu": n_traj, "n_trajectories_total": n_traj * n_gpus,
+            "steps_per_trajectory": sum(2 ** e for e in DT_EXPONENTS), "launches_per_step": len(DT_EXPONENTS),
+            "seed": 0, "outputs": "final t/x/w per trajectory + error moments",
+            "l2": "each launch writes 400 MB of final states (> 126 MB L2); inputs are one 16 B initial condition",
+            "parallelism": f"trajectories sharded over {n_gpus} GPU(s), allreduce of moments"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU port (oracle) - used ONLY as the reported baseline
+# ------------------------------------------------------------------------------------------------
+def _cpu_slab(args):
+    begin, count, n_total, dt_exp = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import problems as oprob, solver as osolver
+    prob = oprob.polar_walk(Y_DRIFT, (2.0, 0.0), TMAX)
+    osolver.solve_many(prob, scheme="wagner_platen", dt=2.0 ** -dt_exp, n_trajectories=n_total, seed=0,
+                       chunk_size=None, dtype=np.float64, traj_slice=(begin, count))
+    return count * 2 ** dt_exp
+
+
+def cpu_port_rate(n_traj, dt_exp, procs):
+    """trajectory-steps/s of the CPU port on `procs` host processes (one slab of trajectories each)."""
+    import multiprocessing as mp
+    per = max(1, n_traj // procs)
+    jobs = [(i * per, per, per * procs, dt_exp) for i in range(procs)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_slab, [(0, 2, 2 * procs, 1)] * procs)       # import / warm-up
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_slab, jobs))
+        el = time.perf_counter() - t0
+    return done / el, el, per * procs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_sample, dt_exp = 125 * procs, 6
+    rates = []
+    for _ in range(args.warmup):
+        cpu_port_rate(max(procs, n_sample // 8), dt_exp, procs)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, el, n_used = cpu_port_rate(n_sample, dt_exp, procs)
+        rates.append(r)
+    total = time.perf_counter() - t_all
+    value = float(np.mean(rates))
+    sample = f"{n_used} trajectories x {2 ** dt_exp} steps (dt=2^-{dt_exp}) of the C2 workload per step, {procs} processes"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(N_TRAJ_PER_GPU, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                             "note": "numpy/torch.func CPU port of the reference (oracle/); JAX is not installable "
+                                     "here, so the reference itself cannot run"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import stochastic_b200 as pychastic
+    import stochastic_b200.numpy as jnp
+    from stochastic_b200 import runtime, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_local = args.n_traj
+    n_total = n_local * world
+    begin = rank * n_local
+
+    problem = workloads.polar_walk(Y_DRIFT, (2.0, 0.0), TMAX, f64=True)
+
+    observables = workloads.polar_error_observables(Y_DRIFT, 2.0)
+
+    solvers = {e: pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=2.0 ** -e) for e in DT_EXPONENTS}
+    steps_per_traj = sum(2 ** e for e in DT_EXPONENTS)
+    x0_pinned = torch.as_tensor(np.asarray(problem.x0)).pin_memory()
+
+    def sweep(e2e=False, host_out=None):
+        """One bench step: the 9-launch dt sweep.  Returns the (9, n_obs, 2) moments tensor."""
+        moms = []
+        for i, e in enumerate(DT_EXPONENTS):
+            if e2e:
+                problem.x0 = x0_pinned.numpy()     # host buffer -> device inside solve_many
+            sol = solvers[e].solve_many(problem, n_trajectories=n_total, seed=0, chunk_size=None,
+                                        progress_bar=False, observables=observables,
+                                        traj_range=(begin, n_local))
+            moms.append(sol["moments"].torch())
+            if e2e:
+                for k, key in enumerate(("time_values", "solution_values", "wiener_values")):
+                    host_out[k].copy_(sol[key].torch().reshape(host_out[k].shape), non_blocking=True)
+        m = torch.stack(moms)
+        if world > 1:
+            dist.all_reduce(m)
+        return m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        out = None
+        for _ in range(k):
+            out = fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # FP64 peak of this device, measured now (roofline denominator)
+    tf, ms_peak = __import__("ctypes").c_double(), __import__("ctypes").c_double()
+    runtime.check(runtime.lib().sdeb200_fp64_peak(8192, tf, ms_peak), "fp64_peak")
+    fp64_peak = tf.value
+
+    for _ in range(args.warmup):
+        sweep()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = runtime.STATS["launches"]
+    ms, moments = timed(sweep, args.steps)
+    launches = runtime.STATS["launches"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_units = float(n_total) * steps_per_traj * args.steps
+    value = total_units / (ms * 1e-3)
+
+    # kernel-only time of the dominant launch (dt = 2^-9), measured live with CUDA events
+    e = DT_EXPONENTS[-1]
+    one = lambda: solvers[e].solve_many(problem, n_trajectories=n_total, seed=0, chunk_size=None, progress_bar=False,
+                                        observables=observables, traj_range=(begin, n_local))
+    one()
+    ms_k, _ = timed(one, 3)
+    ms_k /= 3
+    kernel_rate = n_local * 2 ** e / (ms_k * 1e-3)                 # per GPU
+    achieved = kernel_rate * FLOPS_PER_TRAJ_STEP / 1e12
+
+    # end to end through the public API with host buffers
+    host_out = [torch.empty((n_local, 1), dtype=torch.float64).pin_memory(),
+                torch.empty((n_local, 1, 2), dtype=torch.float64).pin_memory(),
+                torch.empty((n_local, 1, 2), dtype=torch.float64).pin_memory()]
+    sweep(True, host_out)
+    k_e2e = max(1, min(args.steps, 2))
+    ms_e2e, _ = timed(lambda: sweep(True, host_out), k_e2e)
+    e2e_value = float(n_total) * steps_per_traj * k_e2e / (ms_e2e * 1e-3)
+    d2h = sum(t.numel() * 8 for t in host_out) * len(DT_EXPONENTS) + 9 * 2 * 2 * 8
+    h2d = 16 * len(DT_EXPONENTS)
+
+    if rank == 0:
+        mom = moments.cpu().numpy()
+        n_all = float(n_total)
+        strong = (mom[:, 0, 0] / n_all).tolist()
+        weak = (mom[:, 1, 0] / n_all - THEORETICAL_MEAN_PHI).tolist()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            procs = max(1, min(cores, 64))
+            r, el, n_used = cpu_port_rate(125 * procs, 6, procs)
+            cpu = {"value": r, "unit": UNIT, "cores": procs, "kind": "port",
+                   "sample": f"{n_used} trajectories x 64 steps (dt=2^-6) of the same workload, {el:.1f} s, "
+                             f"{procs} processes; numpy/torch.func port of the reference (JAX unavailable)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n_local, world),
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": achieved / fp64_peak, "traffic": None,
+                             "kernel": "sde_solve_kernel (dt=2^-9 launch)", "kernel_ms": ms_k,
+                             "flops_per_trajectory_step": FLOPS_PER_TRAJ_STEP,
+                             "peak_source": "sdeb200_fp64_peak: DFMA loop measured in this run "
+                                            "(MEASURED_PEAKS.json has no FP64 entry)"},
+                "cpu_baseline": cpu,
+                "accuracy": {"dt": [2.0 ** -e for e in DT_EXPONENTS], "mean_strong_error": strong,
+                             "weak_error_mean_phi": weak},
+                "kernel_registers": solvers[e].last_program.info()["registers"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-traj", type=int, default=N_TRAJ_PER_GPU, help="trajectories per GPU (default: 10^7, the BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,26 @@
+"""Package-wide switches (the counterpart of `jax.config`)."""
+
+_STATE = {
+    # Mirrors `jax_enable_x64`: when True, SDEProblem keeps x0 in float64 (the reference casts x0 to
+    # float32 unconditionally, reference pychastic/sde_problem.py:51, and needs x0 overwritten after
+    # construction to run in double precision).
+    "enable_x64": False,
+    # "original": threefry counter layout of jax < 0.5 (jax_threefry_partitionable=False; the layout the
+    # reference's shipped golden trajectories were generated with); "partitionable": jax >= 0.5 default.
+    "prng_layout": "original",
+}
+
+
+def update(name, value):
+    name = name.replace("jax_", "")
+    if name == "threefry_partitionable":
+        name, value = "prng_layout", ("partitionable" if value else "original")
+    if name not in _STATE:
+        raise KeyError(name)
+    if name == "prng_layout" and value not in ("original", "partitionable"):
+        raise ValueError(value)
+    _STATE[name] = value
+
+
+def get(name):
+    return _STATE[name]

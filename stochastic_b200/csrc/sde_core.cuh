@@ -1,0 +1,647 @@
+// sde_core.cuh - device-side building blocks of the batched SDE integrator (sm_100a).
+//
+// Self-contained (no host / libc headers) so that the SAME text is compiled by nvcc at build
+// time and by NVRTC at run time for traced user problems.
+//
+// Replaces, for the hot path of the reference (PyChastic):
+//   * jax.random.{PRNGKey,split,normal}  (reference pychastic/sde_solver.py:223,292,299 and
+//     pychastic/vectorized_I_generation.py:267-349) -> in-register threefry2x32 + Giles erf_inv
+//   * get_wiener_integrals / make_C_mat / make_D_mat
+//     (reference pychastic/vectorized_I_generation.py:22-49,135-236,243-473) -> WienerGen<>
+//
+// Compile-time configuration (macros, defined by the including translation unit):
+//   SDE_M       number of noise terms
+//   SDE_SCHEME  0 euler, 1 milstein, 2 wagner_platen
+//   SDE_P       Fourier series truncation (reference always uses 10, sde_solver.py:271)
+//   SDE_F64     1: double (64 random bits per draw), 0: float (32 random bits per draw)
+//   SDE_LAYOUT  0: original threefry counter layout (jax < 0.5), 1: partitionable (jax >= 0.5)
+#pragma once
+
+#ifndef SDE_P
+#define SDE_P 10
+#endif
+#ifndef SDE_LAYOUT
+#define SDE_LAYOUT 0
+#endif
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+#if SDE_F64
+typedef double real;
+#define RC(x) x
+#else
+typedef float real;
+#define RC(x) x##f
+#endif
+
+#define SDE_EULER 0
+#define SDE_MILSTEIN 1
+#define SDE_WAGNER_PLATEN 2
+
+namespace sdeb {
+
+struct Key {
+    u32 a, b;
+};
+
+// ----------------------------------------------------------------------------------------
+// threefry2x32, 20 rounds (Random123; jax/_src/prng.py::threefry2x32)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 rotl32(u32 x, int r) { return __funnelshift_l(x, x, r); }
+
+__device__ __forceinline__ Key threefry2x32(Key k, u32 x0, u32 x1) {
+    const u32 ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
+    x0 += ks0;
+    x1 += ks1;
+#define TF_ROUND(r) x0 += x1; x1 = rotl32(x1, r); x1 ^= x0;
+    TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+    x0 += ks1; x1 += ks2 + 1u;
+    TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+    x0 += ks2; x1 += ks0 + 2u;
+    TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+    x0 += ks0; x1 += ks1 + 3u;
+    TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+    x0 += ks1; x1 += ks2 + 4u;
+    TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+    x0 += ks2; x1 += ks0 + 5u;
+#undef TF_ROUND
+    Key out;
+    out.a = x0;
+    out.b = x1;
+    return out;
+}
+
+// jax.random.split(key, n)[i].  Original layout: the 2n outputs of
+// threefry_2x32(key, arange(2n)) are [word0(block(k, n+k)) k<n | word1(block(k-n, k)) k>=n],
+// key i = outputs (2i, 2i+1).  Partitionable: both words of block (hi32 i, lo32 i).
+__device__ __forceinline__ u32 split_word(Key key, u64 n, u64 k) {
+    if (k < n) return threefry2x32(key, (u32)k, (u32)(n + k)).a;
+    return threefry2x32(key, (u32)(k - n), (u32)k).b;
+}
+
+__device__ __forceinline__ Key split_key(Key key, u64 n, u64 i) {
+#if SDE_LAYOUT == 0
+    Key out;
+    out.a = split_word(key, n, 2 * i);
+    out.b = split_word(key, n, 2 * i + 1);
+    return out;
+#else
+    return threefry2x32(key, (u32)(i >> 32), (u32)i);
+#endif
+}
+
+// ----------------------------------------------------------------------------------------
+// random bits for element e of a draw of `size` elements (row-major flat index)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 random_bits64(Key key, u32 e, u32 size) {
+#if SDE_LAYOUT == 0
+    Key y = threefry2x32(key, e, size + e);
+#else
+    Key y = threefry2x32(key, 0u, e);
+#endif
+    return ((u64)y.a << 32) | (u64)y.b;
+}
+
+__device__ __forceinline__ u32 random_bits32(Key key, u32 e, u32 size) {
+#if SDE_LAYOUT == 0
+    const u32 h = (size + 1u) >> 1;
+    if (e < h) {
+        u32 c1 = h + e;
+        if (c1 >= size) c1 = 0u;  // odd size: the pad counter
+        return threefry2x32(key, e, c1).a;
+    }
+    return threefry2x32(key, e - h, e).b;
+#else
+    Key y = threefry2x32(key, 0u, e);
+    return y.a ^ y.b;
+#endif
+}
+
+// ----------------------------------------------------------------------------------------
+// erf_inv: XLA's expansion (Giles' polynomials), w = -log1p(-x*x)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float erfinv_xla(float x) {
+    float w = -log1pf(-x * x);
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, w, 3.43273939e-07f);
+        p = fmaf(p, w, -3.5233877e-06f);
+        p = fmaf(p, w, -4.39150654e-06f);
+        p = fmaf(p, w, 0.00021858087f);
+        p = fmaf(p, w, -0.00125372503f);
+        p = fmaf(p, w, -0.00417768164f);
+        p = fmaf(p, w, 0.246640727f);
+        p = fmaf(p, w, 1.50140941f);
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f;
+        p = fmaf(p, w, 0.000100950558f);
+        p = fmaf(p, w, 0.00134934322f);
+        p = fmaf(p, w, -0.00367342844f);
+        p = fmaf(p, w, 0.00573950773f);
+        p = fmaf(p, w, -0.0076224613f);
+        p = fmaf(p, w, 0.00943887047f);
+        p = fmaf(p, w, 1.00167406f);
+        p = fmaf(p, w, 2.83297682f);
+    }
+    return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7f800000) : p * x;
+}
+
+__device__ __forceinline__ double erfinv_xla(double x) {
+    double w = -log1p(-x * x);
+    double p;
+    if (w < 6.25) {
+        w = w - 3.125;
+        p = -3.6444120640178196996e-21;
+        p = fma(p, w, -1.685059138182016589e-19);
+        p = fma(p, w, 1.2858480715256400167e-18);
+        p = fma(p, w, 1.115787767802518096e-17);
+        p = fma(p, w, -1.333171662854620906e-16);
+        p = fma(p, w, 2.0972767875968561637e-17);
+        p = fma(p, w, 6.6376381343583238325e-15);
+        p = fma(p, w, -4.0545662729752068639e-14);
+        p = fma(p, w, -8.1519341976054721522e-14);
+        p = fma(p, w, 2.6335093153082322977e-12);
+        p = fma(p, w, -1.2975133253453532498e-11);
+        p = fma(p, w, -5.4154120542946279317e-11);
+        p = fma(p, w, 1.051212273321532285e-09);
+        p = fma(p, w, -4.1126339803469836976e-09);
+        p = fma(p, w, -2.9070369957882005086e-08);
+        p = fma(p, w, 4.2347877827932403518e-07);
+        p = fma(p, w, -1.3654692000834678645e-06);
+        p = fma(p, w, -1.3882523362786468719e-05);
+        p = fma(p, w, 0.0001867342080340571352);
+        p = fma(p, w, -0.00074070253416626697512);
+        p = fma(p, w, -0.0060336708714301490533);
+        p = fma(p, w, 0.24015818242558961693);
+        p = fma(p, w, 1.6536545626831027356);
+    } else if (w < 16.0) {
+        w = sqrt(w) - 3.25;
+        p = 2.2137376921775787049e-09;
+        p = fma(p, w, 9.0756561938885390979e-08);
+        p = fma(p, w, -2.7517406297064545428e-07);
+        p = fma(p, w, 1.8239629214389227755e-08);
+        p = fma(p, w, 1.5027403968909827627e-06);
+        p = fma(p, w, -4.013867526981545969e-06);
+        p = fma(p, w, 2.9234449089955446044e-06);
+        p = fma(p, w, 1.2475304481671778723e-05);
+        p = fma(p, w, -4.7318229009055733981e-05);
+        p = fma(p, w, 6.8284851459573175448e-05);
+        p = fma(p, w, 2.4031110387097893999e-05);
+        p = fma(p, w, -0.0003550375203628474796);
+        p = fma(p, w, 0.00095328937973738049703);
+        p = fma(p, w, -0.0016882755560235047313);
+        p = fma(p, w, 0.0024914420961078508066);
+        p = fma(p, w, -0.0037512085075692412107);
+        p = fma(p, w, 0.005370914553590063617);
+        p = fma(p, w, 1.0052589676941592334);
+        p = fma(p, w, 3.0838856104922207635);
+    } else {
+        w = sqrt(w) - 5.0;
+        p = -2.7109920616438573243e-11;
+        p = fma(p, w, -2.5556418169965252055e-10);
+        p = fma(p, w, 1.5076572693500548083e-09);
+        p = fma(p, w, -3.7894654401267369937e-09);
+        p = fma(p, w, 7.6157012080783393804e-09);
+        p = fma(p, w, -1.4960026627149240478e-08);
+        p = fma(p, w, 2.9147953450901080826e-08);
+        p = fma(p, w, -6.7711997758452339498e-08);
+        p = fma(p, w, 2.2900482228026654717e-07);
+        p = fma(p, w, -9.9298272942317002539e-07);
+        p = fma(p, w, 4.5260625972231537039e-06);
+        p = fma(p, w, -1.9681778105531670567e-05);
+        p = fma(p, w, 7.5995277030017761139e-05);
+        p = fma(p, w, -0.00021503011930044477347);
+        p = fma(p, w, -0.00013871931833623122026);
+        p = fma(p, w, 1.0103004648645343977);
+        p = fma(p, w, 4.8499064014085844221);
+    }
+    return (fabs(x) == 1.0) ? x * __longlong_as_double(0x7ff0000000000000LL) : p * x;
+}
+
+// jax.random.uniform(key, shape, dtype, nextafter(-1,0), 1) for one element, then
+// jax.random.normal = sqrt(2) * erf_inv(u)
+__device__ __forceinline__ double uniform_pm1(u64 bits) {
+    const double lo = -0.99999999999999988898;  // nextafter(-1, 0)
+    double f = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+    double u = f * (1.0 - lo) + lo;
+    return fmax(lo, u);
+}
+
+__device__ __forceinline__ float uniform_pm1(u32 bits) {
+    const float lo = -0.99999994f;  // nextafter(-1f, 0f)
+    float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+    float u = f * (1.0f - lo) + lo;
+    return fmaxf(lo, u);
+}
+
+// one standard normal: element e of jax.random.normal(key, shape with `size` elements, dtype)
+__device__ __forceinline__ real normal_elem(Key key, u32 e, u32 size) {
+#if SDE_F64
+    return 1.4142135623730951 * erfinv_xla(uniform_pm1(random_bits64(key, e, size)));
+#else
+    return 1.41421354f * erfinv_xla(uniform_pm1(random_bits32(key, e, size)));
+#endif
+}
+
+// ----------------------------------------------------------------------------------------
+// Integrals of one step, already scaled by the powers of dt (reference sde_solver.py:233-241)
+// ----------------------------------------------------------------------------------------
+struct Integrals {
+    real dW[SDE_M];
+#if SDE_SCHEME >= SDE_MILSTEIN
+    real Iww[SDE_M][SDE_M];             // I_(j1,j2)
+#endif
+#if SDE_SCHEME >= SDE_WAGNER_PLATEN
+    real Iwt[SDE_M];                    // I_(j,0)
+    real Itw[SDE_M];                    // I_(0,j)
+    real Iwww[SDE_M][SDE_M][SDE_M];     // I_(j1,j2,j3)
+#endif
+};
+
+struct StepScale {
+    real sqrt_dt;   // sqrt(dt) in the working dtype
+    real dt;
+    real dt32;      // dt**1.5 computed in double on the host, cast
+};
+
+// compile-time helpers ---------------------------------------------------------------------
+#if SDE_P <= 16
+#define SDE_UNROLL _Pragma("unroll")
+#else
+#define SDE_UNROLL _Pragma("unroll 1")
+#endif
+
+// out[l] += sgn * sum_{r=1}^{P-l} X[r] * Y[l+r]      (l = 1..P-1)   arrays indexed 1..P
+__device__ __forceinline__ void acc_corr(const real* X, const real* Y, real* out, const real sgn) {
+    SDE_UNROLL
+    for (int l = 1; l < SDE_P; ++l) {
+        real s = out[l];
+        SDE_UNROLL
+        for (int r = 1; r <= SDE_P - l; ++r) s = fma(sgn * X[r], Y[l + r], s);
+        out[l] = s;
+    }
+}
+
+// out[l] += sgn * sum_{r=1}^{l-1} X[r] * Y[l-r]      (l = 2..P)
+__device__ __forceinline__ void acc_conv(const real* X, const real* Y, real* out, const real sgn) {
+    SDE_UNROLL
+    for (int l = 2; l <= SDE_P; ++l) {
+        real s = out[l];
+        SDE_UNROLL
+        for (int r = 1; r < l; ++r) s = fma(sgn * X[r], Y[l - r], s);
+        out[l] = s;
+    }
+}
+
+__device__ __forceinline__ void zero_arr(real* a) {
+    SDE_UNROLL
+    for (int l = 0; l <= SDE_P; ++l) a[l] = RC(0.0);
+}
+
+// ----------------------------------------------------------------------------------------
+// WienerGen: per-fragment generator.  init(fragment_key, S) once per fragment, then
+// generate(s, scale, I) for step s in [0, S) of that fragment.
+// ----------------------------------------------------------------------------------------
+struct WienerGen {
+    u32 S;
+#if SDE_M == 1 || SDE_SCHEME == SDE_EULER
+    Key k0;
+#elif SDE_SCHEME == SDE_MILSTEIN
+    Key k_xi, k_mu, k_eta, k_zeta;
+#else
+    Key k_xi, k_zeta, k_eta, k_mu, k_phi;
+#endif
+
+    __device__ __forceinline__ void init(Key fkey, u32 steps) {
+        S = steps;
+#if SDE_M == 1 || SDE_SCHEME == SDE_EULER
+        k0 = fkey;
+#elif SDE_SCHEME == SDE_MILSTEIN
+        k_xi = split_key(fkey, 4, 0);
+        k_mu = split_key(fkey, 4, 1);
+        k_eta = split_key(fkey, 4, 2);
+        k_zeta = split_key(fkey, 4, 3);
+#else
+        k_xi = split_key(fkey, 5, 0);
+        k_zeta = split_key(fkey, 5, 1);
+        k_eta = split_key(fkey, 5, 2);
+        k_mu = split_key(fkey, 5, 3);
+        k_phi = split_key(fkey, 5, 4);
+#endif
+    }
+
+    __device__ __forceinline__ void generate(u32 s, const StepScale& sc, Integrals& I) const {
+#if SDE_M == 1
+        // closed forms, reference vectorized_I_generation.py:265-294
+#if SDE_SCHEME == SDE_WAGNER_PLATEN
+        const real u0 = normal_elem(k0, s, 2u * S);
+        const real u1 = normal_elem(k0, S + s, 2u * S);
+        const real dZ = RC(0.5) * (u0 + RC(0.57735026918962576451) * u1);
+        I.dW[0] = sc.sqrt_dt * u0;
+        I.Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
+        I.Iwt[0] = sc.dt32 * dZ;
+        I.Itw[0] = sc.dt32 * (u0 - dZ);
+        I.Iwww[0][0][0] = sc.dt32 * (RC(0.5) * (RC(0.33333333333333333333) * u0 * u0 - RC(1.0)) * u0);
+#else
+        const real u0 = normal_elem(k0, s, S);
+        I.dW[0] = sc.sqrt_dt * u0;
+#if SDE_SCHEME == SDE_MILSTEIN
+        I.Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
+#endif
+#endif
+#elif SDE_SCHEME == SDE_EULER
+#pragma unroll
+        for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * normal_elem(k0, s * SDE_M + j, S * SDE_M);
+#elif SDE_SCHEME == SDE_MILSTEIN
+        gen_milstein(s, sc, I);
+#else
+        gen_wagner_platen(s, sc, I);
+#endif
+    }
+
+#if SDE_M > 1 && SDE_SCHEME == SDE_MILSTEIN
+    // reference vectorized_I_generation.py:301-339 (Kloeden-Platen 10.3.7, truncated at p)
+    __device__ __forceinline__ void gen_milstein(u32 s, const StepScale& sc, Integrals& I) const {
+        constexpr int M = SDE_M, P = SDE_P;
+        real xi[M], mu[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            xi[j] = normal_elem(k_xi, s * M + j, S * M);
+            mu[j] = normal_elem(k_mu, s * M + j, S * M);
+        }
+        real ser[M][M];  // upper triangle: sum_r (1/r) (zeta_ri a_rj - a_ri zeta_rj)
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) ser[i][j] = RC(0.0);
+        SDE_UNROLL
+        for (int r = 1; r <= P; ++r) {
+            real a[M], z[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const u32 e = (s * P + (r - 1)) * M + j;
+                a[j] = fma(RC(1.4142135623730950488), xi[j], normal_elem(k_eta, e, S * P * M));
+                z[j] = normal_elem(k_zeta, e, S * P * M);
+            }
+            const real rec = RC(1.0) / (real)r;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = i + 1; j < M; ++j) ser[i][j] = fma(rec, z[i] * a[j] - a[i] * z[j], ser[i][j]);
+        }
+        real rho = RC(0.0);
+        SDE_UNROLL
+        for (int r = 1; r <= P; ++r) rho += RC(1.0) / (real)(r * r);
+        rho = RC(0.083333333333333333333) - rho * RC(0.050660591821168885722);  // 1/12 - sum/(2 pi^2)
+        const real sqrt_rho = sqrt(rho);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            I.dW[i] = sc.sqrt_dt * xi[i];
+            I.Iww[i][i] = sc.dt * (RC(0.5) * (xi[i] * xi[i] - RC(1.0)));
+#pragma unroll
+            for (int j = i + 1; j < M; ++j) {
+                const real sym = RC(0.5) * xi[i] * xi[j];
+                const real asym = sqrt_rho * (xi[i] * mu[j] - mu[i] * xi[j]) +
+                                  RC(0.15915494309189533577) * ser[i][j];
+                I.Iww[i][j] = sc.dt * (sym + asym);
+                I.Iww[j][i] = sc.dt * (sym - asym);
+            }
+        }
+    }
+#endif
+
+#if SDE_M > 1 && SDE_SCHEME == SDE_WAGNER_PLATEN
+    // reference vectorized_I_generation.py:340-470 (Kloeden-Platen 5.8.11 / 10.4.7)
+    // Works on the prescaled series coefficients zs[j][r] = zeta_{r,j}/r, es[j][r] = eta_{r,j}/r,
+    // which turns every term of the C and D double sums into a single FMA, and shares the
+    // correlation / convolution partial sums between D[j1,.,j3] and D[j3,.,j1].
+    __device__ __forceinline__ void gen_wagner_platen(u32 s, const StepScale& sc, Integrals& I) const {
+        constexpr int M = SDE_M, P = SDE_P;
+        const real PI = RC(3.14159265358979323846);
+        real xi[M], a[M], b[M];
+        real zs[M][P + 1], es[M][P + 1];
+        {
+            real sa[M], sb[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) { sa[j] = RC(0.0); sb[j] = RC(0.0); zs[j][0] = RC(0.0); es[j][0] = RC(0.0); }
+            SDE_UNROLL
+            for (int r = 1; r <= P; ++r) {
+                const real rec = RC(1.0) / (real)r;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const u32 e = (s * P + (r - 1)) * M + j;
+                    const real z = rec * normal_elem(k_zeta, e, S * P * M);
+                    const real h = rec * normal_elem(k_eta, e, S * P * M);
+                    zs[j][r] = z;
+                    es[j][r] = h;
+                    sa[j] += z;                       // sum zeta_r / r
+                    sb[j] = fma(rec, h, sb[j]);       // sum eta_r / r^2
+                }
+            }
+            real rho = RC(0.0), alpha = RC(0.0);
+            SDE_UNROLL
+            for (int r = 1; r <= P; ++r) {
+                const real r2 = RC(1.0) / (real)(r * r);
+                rho += r2;
+                alpha += r2 * r2;
+            }
+            rho = RC(0.083333333333333333333) - rho * RC(0.050660591821168885722);      // 1/12 - sum/(2 pi^2)
+            alpha = RC(0.054831135561607547882) - alpha * RC(0.050660591821168885722);  // pi^2/180 - sum/(2 pi^2)
+            const real two_sqrt_rho = RC(2.0) * sqrt(rho), sqrt_alpha = sqrt(alpha);
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                xi[j] = normal_elem(k_xi, s * M + j, S * M);
+                const real mu = normal_elem(k_mu, s * M + j, S * M);
+                const real phi = normal_elem(k_phi, s * M + j, S * M);
+                a[j] = -RC(0.45015815807855303478) * sa[j] - two_sqrt_rho * mu;   // sqrt(2)/pi
+                b[j] = fma(RC(0.22507907903927651739), sb[j], sqrt_alpha * phi);  // 1/(sqrt(2) pi)
+            }
+        }
+
+        // A (antisymmetric), B (symmetric)
+        real A[M][M], B[M][M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+#pragma unroll
+            for (int j = i; j < M; ++j) {
+                real sA = RC(0.0), sB = RC(0.0);
+                SDE_UNROLL
+                for (int r = 1; r <= P; ++r) {
+                    sB = fma(zs[i][r], zs[j][r], sB);
+                    sB = fma(es[i][r], es[j][r], sB);
+                    if (j > i) sA = fma((real)r * zs[i][r], es[j][r], fma(-(real)r * es[i][r], zs[j][r], sA));
+                }
+                B[i][j] = B[j][i] = RC(0.025330295910584442861) * sB;     // 1/(4 pi^2)
+                A[i][j] = RC(0.15915494309189533577) * sA;                // 1/(2 pi)
+                A[j][i] = -A[i][j];
+            }
+        }
+
+        // C[j1][j2] = -1/(2 pi^2) sum_{l != r} [ r^2/(r^2-l^2) zs[j1][r] zs[j2][l] + r l/(r^2-l^2) es[j1][r] es[j2][l] ]
+        real C[M][M];
+#pragma unroll
+        for (int j1 = 0; j1 < M; ++j1) {
+            real Uz[P + 1], Ue[P + 1];
+            SDE_UNROLL
+            for (int l = 1; l <= P; ++l) {
+                real uz = RC(0.0), ue = RC(0.0);
+                SDE_UNROLL
+                for (int r = 1; r <= P; ++r) {
+                    if (r != l) {
+                        uz = fma((real)(r * r) / (real)(r * r - l * l), zs[j1][r], uz);
+                        ue = fma((real)(r * l) / (real)(r * r - l * l), es[j1][r], ue);
+                    }
+                }
+                Uz[l] = uz;
+                Ue[l] = ue;
+            }
+#pragma unroll
+            for (int j2 = 0; j2 < M; ++j2) {
+                real c = RC(0.0);
+                SDE_UNROLL
+                for (int l = 1; l <= P; ++l) c = fma(zs[j2][l], Uz[l], fma(es[j2][l], Ue[l], c));
+                C[j1][j2] = -RC(0.050660591821168885722) * c;
+            }
+        }
+
+        // D[j1][j2][j3] = K sum_l ( zs[j2][l] Tz_{j1 j3}[l] + es[j2][l] Te_{j1 j3}[l] ), the factor l
+        // that undoes the prescaling of the j2 coefficient is folded into Tz / Te.
+        real D[M][M][M];
+        const real KD = RC(0.017911224018155010247);  // 1 / (pi^2 2^(5/2))
+#pragma unroll
+        for (int ja = 0; ja < M; ++ja) {
+            {   // j1 = j3 = ja:  Tz = 2 (corr_ze - corr_ez + conv_ze),  Te = conv_ee - conv_zz
+                real Tz[P + 1], Te[P + 1];
+                zero_arr(Tz);
+                zero_arr(Te);
+                acc_corr(zs[ja], es[ja], Tz, RC(1.0));
+                acc_corr(es[ja], zs[ja], Tz, -RC(1.0));
+                acc_conv(zs[ja], es[ja], Tz, RC(1.0));
+                acc_conv(es[ja], es[ja], Te, RC(1.0));
+                acc_conv(zs[ja], zs[ja], Te, -RC(1.0));
+                SDE_UNROLL
+                for (int l = 1; l <= P; ++l) {
+                    Tz[l] *= (real)(2 * l);
+                    Te[l] *= (real)l;
+                }
+#pragma unroll
+                for (int j2 = 0; j2 < M; ++j2) {
+                    real d = RC(0.0);
+                    SDE_UNROLL
+                    for (int l = 1; l <= P; ++l) d = fma(zs[j2][l], Tz[l], fma(es[j2][l], Te[l], d));
+                    D[ja][j2][ja] = KD * d;
+                }
+            }
+#pragma unroll
+            for (int jb = ja + 1; jb < M; ++jb) {
+                real dab[M], dba[M];
+                {
+                    // Tz(a,b) = Q + 2 corr_ze[b,a],  Tz(b,a) = Q + 2 corr_ze[a,b]
+                    // Q = conv_ze[a,b] + conv_ze[b,a] - corr_ez[a,b] - corr_ez[b,a]
+                    real Q[P + 1], R1[P + 1], R2[P + 1];
+                    zero_arr(Q);
+                    zero_arr(R1);
+                    zero_arr(R2);
+                    acc_corr(es[ja], zs[jb], Q, -RC(1.0));
+                    acc_corr(es[jb], zs[ja], Q, -RC(1.0));
+                    acc_conv(zs[ja], es[jb], Q, RC(1.0));
+                    acc_conv(zs[jb], es[ja], Q, RC(1.0));
+                    acc_corr(zs[jb], es[ja], R1, RC(1.0));
+                    acc_corr(zs[ja], es[jb], R2, RC(1.0));
+                    SDE_UNROLL
+                    for (int l = 1; l <= P; ++l) {
+                        const real ql = (real)l * Q[l];
+                        R1[l] = fma((real)(2 * l), R1[l], ql);
+                        R2[l] = fma((real)(2 * l), R2[l], ql);
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < M; ++j2) {
+                        real d1 = RC(0.0), d2 = RC(0.0);
+                        SDE_UNROLL
+                        for (int l = 1; l <= P; ++l) {
+                            d1 = fma(zs[j2][l], R1[l], d1);
+                            d2 = fma(zs[j2][l], R2[l], d2);
+                        }
+                        dab[j2] = d1;
+                        dba[j2] = d2;
+                    }
+                }
+                {
+                    // Te(a,b) = W + V, Te(b,a) = W - V
+                    // V = corr_zz[b,a] - corr_zz[a,b] + corr_ee[b,a] - corr_ee[a,b],  W = conv_ee[a,b] - conv_zz[a,b]
+                    real V[P + 1], W[P + 1];
+                    zero_arr(V);
+                    zero_arr(W);
+                    acc_corr(zs[jb], zs[ja], V, RC(1.0));
+                    acc_corr(zs[ja], zs[jb], V, -RC(1.0));
+                    acc_corr(es[jb], es[ja], V, RC(1.0));
+                    acc_corr(es[ja], es[jb], V, -RC(1.0));
+                    acc_conv(es[ja], es[jb], W, RC(1.0));
+                    acc_conv(zs[ja], zs[jb], W, -RC(1.0));
+                    SDE_UNROLL
+                    for (int l = 1; l <= P; ++l) {
+                        const real pw = (real)l * W[l], qv = (real)l * V[l];
+                        V[l] = pw + qv;
+                        W[l] = pw - qv;
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < M; ++j2) {
+                        real d1 = dab[j2], d2 = dba[j2];
+                        SDE_UNROLL
+                        for (int l = 1; l <= P; ++l) {
+                            d1 = fma(es[j2][l], V[l], d1);
+                            d2 = fma(es[j2][l], W[l], d2);
+                        }
+                        D[ja][j2][jb] = KD * d1;
+                        D[jb][j2][ja] = KD * d2;
+                    }
+                }
+            }
+        }
+
+        // assembly, reference vectorized_I_generation.py:393-470
+        real wt[M], tw[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            wt[j] = RC(0.5) * (xi[j] + a[j]);
+            tw[j] = xi[j] - wt[j];
+            I.dW[j] = sc.sqrt_dt * xi[j];
+            I.Iwt[j] = sc.dt32 * wt[j];
+            I.Itw[j] = sc.dt32 * tw[j];
+        }
+        real Jww[M][M], Jtww[M][M];
+        const real inv_pi = RC(0.31830988618379067154);
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const real xx = xi[i] * xi[j];
+                Jww[i][j] = RC(0.5) * xx - RC(0.5) * (xi[i] * a[j] - xi[j] * a[i]) + A[i][j];
+                Jtww[i][j] = RC(0.16666666666666666667) * xx - inv_pi * xi[j] * b[i] + B[i][j] -
+                             RC(0.25) * a[j] * xi[i] + RC(0.5) * inv_pi * xi[i] * b[j] + C[i][j] +
+                             RC(0.5) * A[i][j];
+                I.Iww[i][j] = sc.dt * ((i == j) ? RC(0.5) * (xx - RC(1.0)) : Jww[i][j]);
+            }
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    real J = xi[i] * Jtww[j][k] + RC(0.5) * a[i] * Jww[j][k] +
+                             RC(0.5) * inv_pi * b[i] * xi[j] * xi[k] - xi[j] * B[i][k] +
+                             xi[k] * (RC(0.5) * A[i][j] - C[j][i]) + D[i][j][k];
+                    if (i == j) J -= RC(0.5) * tw[k];
+                    if (j == k) J -= RC(0.5) * wt[i];
+                    I.Iwww[i][j][k] = sc.dt32 * J;
+                }
+        (void)PI;
+    }
+#endif
+};
+
+}  // namespace sdeb

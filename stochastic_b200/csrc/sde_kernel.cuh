@@ -1,0 +1,137 @@
+// sde_kernel.cuh - the trajectory-stepping kernel (one thread per trajectory, state and step
+// loop in registers, only requested snapshots written out).
+//
+// Replaces the vmapped 3-level lax.scan nest of the reference
+// (pychastic/sde_solver.py:228-300: scan_func / chunk_function / get_solution_fragment /
+// get_solution + vmap) for low-dimensional problems.
+//
+// Included AFTER sde_core.cuh and after the problem's device functions:
+//   __device__ void sde_step(real (&x)[SDE_D], const sdeb::Integrals& I, real dt);   // required
+//   __device__ void sde_post(real (&x)[SDE_D]);                      // if SDE_HAS_POST
+//   __device__ void sde_observe(const real*, const real*, real, double (&obs)[SDE_NOBS]);  // if SDE_NOBS > 0
+#pragma once
+
+#ifndef SDE_BLOCK
+#define SDE_BLOCK 128
+#endif
+#ifndef SDE_NOBS
+#define SDE_NOBS 0
+#endif
+#ifndef SDE_HAS_POST
+#define SDE_HAS_POST 0
+#endif
+
+namespace sdeb {
+
+// Plain-old-data argument block; mirrored field by field by `sdeb200_solve_args_t`
+// in include/sdeb200.h (the host copies it into the kernel parameter space).
+struct SolveArgs {
+    u32 key_a, key_b;         // jax.random.PRNGKey(seed)
+    u32 n_fragments;          // number_of_chunks // chunks_per_randomization
+    u32 cpr;                  // chunks per randomization (chunks per fragment)
+    u32 chunk;                // steps per chunk
+    u32 n_snapshots;          // chunks actually integrated and stored per trajectory (<= n_fragments*cpr)
+    u64 n_traj_total;         // N of split(PRNGKey(seed), N): decides every trajectory key
+    u64 traj_begin;           // global index of this launch's first trajectory
+    u64 traj_count;           // trajectories in this launch
+    const real* x0;           // initial conditions of this launch's trajectories
+    long long x0_stride;      // elements between consecutive ICs (0: one IC broadcast)
+    double dt;                // step
+    double dt32;              // dt ** 1.5 (evaluated in double on the host, as the reference does)
+    real* out_t;              // (traj_count, n_snapshots)            or nullptr
+    real* out_x;              // (traj_count, n_snapshots, SDE_D)     or nullptr
+    real* out_w;              // (traj_count, n_snapshots, SDE_M)     or nullptr
+    double* moments;          // (SDE_NOBS, 2): sum, sum of squares   or nullptr
+};
+
+}  // namespace sdeb
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_solve_kernel(const sdeb::SolveArgs A) {
+    using namespace sdeb;
+    const u64 tid = (u64)blockIdx.x * SDE_BLOCK + threadIdx.x;
+    const bool active = tid < A.traj_count;
+#if SDE_NOBS > 0
+    double obs[SDE_NOBS];
+#pragma unroll
+    for (int k = 0; k < SDE_NOBS; ++k) obs[k] = 0.0;
+#else
+    if (!active) return;
+#endif
+    if (active) {
+        Key root;
+        root.a = A.key_a;
+        root.b = A.key_b;
+        const Key tkey = split_key(root, A.n_traj_total, A.traj_begin + tid);
+
+        real x[SDE_D], w[SDE_M];
+        real t = RC(0.0);
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) x[i] = A.x0[tid * (u64)A.x0_stride + i];
+#pragma unroll
+        for (int j = 0; j < SDE_M; ++j) w[j] = RC(0.0);
+
+        StepScale sc;
+        sc.dt = (real)A.dt;
+        sc.sqrt_dt = sqrt((real)A.dt);
+        sc.dt32 = (real)A.dt32;
+        const u32 S = A.chunk * A.cpr;
+        u32 snap = 0;
+        for (u32 f = 0; f < A.n_fragments && snap < A.n_snapshots; ++f) {
+            WienerGen gen;
+            gen.init(split_key(tkey, A.n_fragments, f), S);
+            u32 s = 0;
+            for (u32 c = 0; c < A.cpr && snap < A.n_snapshots; ++c, ++snap) {
+                for (u32 k = 0; k < A.chunk; ++k, ++s) {
+                    Integrals I;
+                    gen.generate(s, sc, I);
+                    t += sc.dt;
+                    sde_step(x, I, sc.dt);
+#if SDE_HAS_POST
+                    sde_post(x);
+#endif
+#pragma unroll
+                    for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
+                }
+                const u64 row = tid * (u64)A.n_snapshots + snap;
+                if (A.out_t) A.out_t[row] = t;
+                if (A.out_x) {
+#pragma unroll
+                    for (int i = 0; i < SDE_D; ++i) A.out_x[row * SDE_D + i] = x[i];
+                }
+                if (A.out_w) {
+#pragma unroll
+                    for (int j = 0; j < SDE_M; ++j) A.out_w[row * SDE_M + j] = w[j];
+                }
+            }
+        }
+#if SDE_NOBS > 0
+        sde_observe(x, w, t, obs);
+#endif
+    }
+#if SDE_NOBS > 0
+    // block reduction of sum and sum of squares, one atomicAdd pair per observable per block
+    __shared__ double red[2 * SDE_NOBS][SDE_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < SDE_NOBS; ++k) {
+        double s1 = active ? obs[k] : 0.0;
+        double s2 = s1 * s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            red[2 * k][wid] = s1;
+            red[2 * k + 1][wid] = s2;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * SDE_NOBS && A.moments) {
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < SDE_BLOCK / 32; ++v) s += red[threadIdx.x][v];
+        atomicAdd(&A.moments[threadIdx.x], s);
+    }
+#endif
+}

@@ -1,0 +1,316 @@
+// sdeb200.cu - host side of the C ABI declared in include/sdeb200.h.
+//
+// * NVRTC compilation of emitted problem sources for sm_100a (no GPU needed),
+// * cubin loading / kernel launch through the CUDA driver API (libcuda is dlopen'ed lazily so
+//   the library also loads on a CPU-only box for symbol checks),
+// * a measured FP64-FMA peak micro-benchmark (the roofline denominator).
+//
+// The helper kernels for isolated PRNG parity checks live in sde_helpers.cu (one object per
+// dtype/layout combination).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sdeb200.h"
+
+static_assert(sizeof(sdeb200_solve_args_t) == 112, "sdeb200_solve_args_t layout");
+static_assert(sizeof(sdeb200_wiener_args_t) == 56, "sdeb200_wiener_args_t layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+// ---- lazily bound driver API -----------------------------------------------------------
+struct Driver {
+    void* lib = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+Driver& driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!d.lib) {
+            d.why = std::string("cannot load libcuda.so.1: ") + dlerror();
+            return;
+        }
+#define BIND(field, sym)                                              \
+    d.field = reinterpret_cast<decltype(d.field)>(dlsym(d.lib, sym)); \
+    if (!d.field) {                                                   \
+        d.why = std::string("missing driver symbol ") + sym;          \
+        return;                                                       \
+    }
+        BIND(ModuleLoadData, "cuModuleLoadData")
+        BIND(ModuleUnload, "cuModuleUnload")
+        BIND(ModuleGetFunction, "cuModuleGetFunction")
+        BIND(LaunchKernel, "cuLaunchKernel")
+        BIND(FuncGetAttribute, "cuFuncGetAttribute")
+        BIND(GetErrorString, "cuGetErrorString")
+#undef BIND
+        d.ok = true;
+    });
+    return d;
+}
+
+std::string cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (driver().ok) driver().GetErrorString(r, &s);
+    return std::string(s ? s : "unknown CUDA driver error") + " (" + std::to_string((int)r) + ")";
+}
+
+}  // namespace
+
+struct sdeb200_program {
+    CUmodule module = nullptr;
+    CUfunction func = nullptr;
+};
+
+extern "C" {
+
+int sdeb200_abi_version(void) { return SDEB200_ABI_VERSION; }
+
+const char* sdeb200_last_error(void) { return g_err.c_str(); }
+
+void sdeb200_free(void* p) { free(p); }
+
+int sdeb200_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(1, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    e = cudaFree(nullptr);  // force creation of the primary context and make it current
+    if (e != cudaSuccess) return fail(1, std::string("context init: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int sdeb200_compile(const char* source, const char* include_dir, const char* arch, void** cubin,
+                    size_t* cubin_size, char** log) {
+    if (!source || !cubin || !cubin_size) return fail(-1, "sdeb200_compile: null argument");
+    *cubin = nullptr;
+    *cubin_size = 0;
+    if (log) *log = nullptr;
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, source, "sde_problem.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(2, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
+    std::string a = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
+    std::string inc = std::string("--include-path=") + (include_dir ? include_dir : ".");
+    std::vector<const char*> opts = {a.c_str(), inc.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
+                                     "-default-device"};
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string log_text(log_size, '\0');
+    if (log_size > 1) nvrtcGetProgramLog(prog, &log_text[0]);
+    if (log && log_size > 1) {
+        *log = (char*)malloc(log_size + 1);
+        memcpy(*log, log_text.c_str(), log_size);
+        (*log)[log_size] = 0;
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(2, std::string("nvrtcCompileProgram: ") + nvrtcGetErrorString(r) + "\n" + log_text);
+    }
+    size_t n = 0;
+    r = nvrtcGetCUBINSize(prog, &n);
+    if (r != NVRTC_SUCCESS || n == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(2, std::string("nvrtcGetCUBINSize: ") + nvrtcGetErrorString(r));
+    }
+    void* buf = malloc(n);
+    r = nvrtcGetCUBIN(prog, (char*)buf);
+    nvrtcDestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS) {
+        free(buf);
+        return fail(2, std::string("nvrtcGetCUBIN: ") + nvrtcGetErrorString(r));
+    }
+    *cubin = buf;
+    *cubin_size = n;
+    return 0;
+}
+
+int sdeb200_program_load(const void* cubin, size_t cubin_size, const char* entry, sdeb200_program_t** out) {
+    if (!cubin || !cubin_size || !entry || !out) return fail(-1, "sdeb200_program_load: null argument");
+    Driver& d = driver();
+    if (!d.ok) return fail(3, d.why);
+    cudaError_t e = cudaFree(nullptr);
+    if (e != cudaSuccess) return fail(1, std::string("no CUDA context: ") + cudaGetErrorString(e));
+    sdeb200_program* p = new sdeb200_program();
+    CUresult r = d.ModuleLoadData(&p->module, cubin);
+    if (r != CUDA_SUCCESS) {
+        delete p;
+        return fail(3, "cuModuleLoadData: " + cu_err(r));
+    }
+    r = d.ModuleGetFunction(&p->func, p->module, entry);
+    if (r != CUDA_SUCCESS) {
+        d.ModuleUnload(p->module);
+        delete p;
+        return fail(3, std::string("cuModuleGetFunction(") + entry + "): " + cu_err(r));
+    }
+    *out = p;
+    return 0;
+}
+
+int sdeb200_program_destroy(sdeb200_program_t* prog) {
+    if (!prog) return 0;
+    if (prog->module && driver().ok) driver().ModuleUnload(prog->module);
+    delete prog;
+    return 0;
+}
+
+int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, int* max_threads) {
+    if (!prog) return fail(-1, "sdeb200_program_info: null program");
+    Driver& d = driver();
+    if (regs) d.FuncGetAttribute(regs, CU_FUNC_ATTRIBUTE_NUM_REGS, prog->func);
+    if (smem_bytes) d.FuncGetAttribute(smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, prog->func);
+    if (max_threads) d.FuncGetAttribute(max_threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, prog->func);
+    return 0;
+}
+
+int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, void* stream) {
+    if (!prog || !args) return fail(-1, "sdeb200_solve: null argument");
+    if (block <= 0 || block > 1024 || (block % 32)) return fail(-1, "sdeb200_solve: bad block size");
+    if (args->traj_count == 0) return 0;
+    if (!args->x0) return fail(-1, "sdeb200_solve: x0 is NULL");
+    if (args->traj_begin + args->traj_count > args->n_traj_total)
+        return fail(-1, "sdeb200_solve: trajectory range exceeds n_traj_total");
+    if (args->n_fragments == 0 || args->cpr == 0 || args->chunk == 0)
+        return fail(-1, "sdeb200_solve: n_fragments, cpr and chunk must be positive");
+    if ((uint64_t)args->n_snapshots > (uint64_t)args->n_fragments * args->cpr)
+        return fail(-1, "sdeb200_solve: n_snapshots exceeds n_fragments * cpr");
+    if (!(args->dt > 0)) return fail(-1, "sdeb200_solve: dt must be positive");
+    uint64_t grid = (args->traj_count + (uint64_t)block - 1) / (uint64_t)block;
+    if (grid > 0x7fffffffULL) return fail(-1, "sdeb200_solve: too many trajectories for one launch");
+    sdeb200_solve_args_t a = *args;
+    void* params[] = {&a};
+    CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0,
+                                       (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_solve_kernel): " + cu_err(r));
+    return 0;
+}
+
+int sdeb200_wiener_integrals(sdeb200_program_t* prog, const sdeb200_wiener_args_t* args, int block,
+                             void* stream) {
+    if (!prog || !args) return fail(-1, "sdeb200_wiener_integrals: null argument");
+    if (args->steps == 0) return 0;
+    if (!args->d_w) return fail(-1, "sdeb200_wiener_integrals: d_w is NULL");
+    unsigned grid = (args->steps + (unsigned)block - 1) / (unsigned)block;
+    sdeb200_wiener_args_t a = *args;
+    void* params[] = {&a};
+    CUresult r = driver().LaunchKernel(prog->func, grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream,
+                                       params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_wiener_kernel): " + cu_err(r));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- FP64 FMA peak ------------------------------------------------------------------------
+// 8 independent FMA chains per thread, 1024 threads/SM resident: enough to saturate the DFMA pipe.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+extern "C" int sdeb200_fp64_peak(int iters, double* tflops, double* elapsed_ms) {
+    if (iters <= 0) iters = 4096;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(1, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* out = nullptr;
+    e = cudaMalloc(&out, sizeof(double));
+    if (e != cudaSuccess) return fail(1, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters / 8 + 1, 0.999999, 1e-7);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(1, std::string("fp64_peak_kernel: ") + cudaGetErrorString(e));
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (elapsed_ms) *elapsed_ms = best;
+    return 0;
+}
+
+// ---- PRNG helper dispatch (kernels in sde_helpers.cu, one object per dtype/layout) -----------
+#define DECL_HELPERS(sfx)                                                                                 \
+    extern "C" int sdeb200_keys_split_##sfx(unsigned, unsigned, unsigned long long, unsigned long long,   \
+                                            unsigned long long, unsigned*, void*);                        \
+    extern "C" int sdeb200_normal_##sfx(unsigned, unsigned, unsigned long long, void*, void*);
+DECL_HELPERS(f32_l0)
+DECL_HELPERS(f32_l1)
+DECL_HELPERS(f64_l0)
+DECL_HELPERS(f64_l1)
+
+extern "C" int sdeb200_keys_split(uint32_t key_a, uint32_t key_b, uint64_t n_total, uint64_t begin, uint64_t count,
+                                  int layout, uint32_t* out_keys, void* stream) {
+    if (count == 0) return 0;
+    if (!out_keys) return fail(-1, "sdeb200_keys_split: out_keys is NULL");
+    if (begin + count > n_total) return fail(-1, "sdeb200_keys_split: range exceeds n_total");
+    if (layout == 0 && 2 * n_total > 0x100000000ULL)
+        return fail(-1, "sdeb200_keys_split: original layout needs 2*n_total <= 2^32");
+    int e = (layout == 0) ? sdeb200_keys_split_f64_l0(key_a, key_b, n_total, begin, count, out_keys, stream)
+          : (layout == 1) ? sdeb200_keys_split_f64_l1(key_a, key_b, n_total, begin, count, out_keys, stream)
+                          : -1;
+    if (e < 0) return fail(-1, "sdeb200_keys_split: unknown layout");
+    if (e) return fail(1, std::string("keys_split_kernel: ") + cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+extern "C" int sdeb200_normal(uint32_t key_a, uint32_t key_b, uint64_t n, int dtype_f64, int layout, void* out,
+                              void* stream) {
+    if (n == 0) return 0;
+    if (!out) return fail(-1, "sdeb200_normal: out is NULL");
+    if (layout != 0 && layout != 1) return fail(-1, "sdeb200_normal: unknown layout");
+    if (n > 0x7fffffffULL) return fail(-1, "sdeb200_normal: n too large");
+    int e;
+    if (dtype_f64)
+        e = layout ? sdeb200_normal_f64_l1(key_a, key_b, n, out, stream) : sdeb200_normal_f64_l0(key_a, key_b, n, out, stream);
+    else
+        e = layout ? sdeb200_normal_f32_l1(key_a, key_b, n, out, stream) : sdeb200_normal_f32_l0(key_a, key_b, n, out, stream);
+    if (e) return fail(1, std::string("normal_kernel: ") + cudaGetErrorString((cudaError_t)e));
+    return 0;
+}

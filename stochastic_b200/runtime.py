@@ -1,0 +1,211 @@
+"""ctypes binding of libsdeb200.so (C ABI in include/sdeb200.h) + compiled-program cache.
+
+There is NO CPU fallback: every compute entry point raises if the library or a CUDA device
+is missing.  NVRTC compilation needs no GPU, so `compile_source` also works on a CPU-only
+box (used by `__graft_entry__.build()` to pre-populate the cubin cache that travels to the
+GPU box).
+"""
+import ctypes
+import hashlib
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdeb200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+CACHE_DIR = os.environ.get("SDEB200_CACHE_DIR", os.path.join(_HERE, "_cubin_cache"))
+
+EXPORTS = (
+    "sdeb200_abi_version", "sdeb200_last_error", "sdeb200_set_device", "sdeb200_compile", "sdeb200_free",
+    "sdeb200_program_load", "sdeb200_program_destroy", "sdeb200_program_info", "sdeb200_solve",
+    "sdeb200_wiener_integrals", "sdeb200_keys_split", "sdeb200_normal", "sdeb200_fp64_peak",
+)
+
+
+class SolveArgs(ctypes.Structure):
+    """Mirror of `sdeb200_solve_args_t`."""
+    _fields_ = [
+        ("key_a", ctypes.c_uint32), ("key_b", ctypes.c_uint32),
+        ("n_fragments", ctypes.c_uint32), ("cpr", ctypes.c_uint32),
+        ("chunk", ctypes.c_uint32), ("n_snapshots", ctypes.c_uint32),
+        ("n_traj_total", ctypes.c_uint64), ("traj_begin", ctypes.c_uint64), ("traj_count", ctypes.c_uint64),
+        ("x0", ctypes.c_void_p), ("x0_stride", ctypes.c_int64),
+        ("dt", ctypes.c_double), ("dt32", ctypes.c_double),
+        ("out_t", ctypes.c_void_p), ("out_x", ctypes.c_void_p), ("out_w", ctypes.c_void_p),
+        ("moments", ctypes.c_void_p),
+    ]
+
+
+class WienerArgs(ctypes.Structure):
+    """Mirror of `sdeb200_wiener_args_t`."""
+    _fields_ = [
+        ("key_a", ctypes.c_uint32), ("key_b", ctypes.c_uint32), ("steps", ctypes.c_uint32), ("_pad", ctypes.c_uint32),
+        ("d_w", ctypes.c_void_p), ("d_ww", ctypes.c_void_p), ("d_wt", ctypes.c_void_p), ("d_tw", ctypes.c_void_p),
+        ("d_www", ctypes.c_void_p),
+    ]
+
+
+assert ctypes.sizeof(SolveArgs) == 112 and ctypes.sizeof(WienerArgs) == 56
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class Sdeb200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libsdeb200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise Sdeb200Error(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C stochastic_b200/csrc`). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.sdeb200_last_error.restype = ctypes.c_char_p
+        L.sdeb200_compile.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                      ctypes.POINTER(ctypes.c_void_p)]
+        L.sdeb200_free.argtypes = [ctypes.c_void_p]
+        L.sdeb200_free.restype = None
+        L.sdeb200_program_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                           ctypes.POINTER(ctypes.c_void_p)]
+        L.sdeb200_program_destroy.argtypes = [ctypes.c_void_p]
+        L.sdeb200_program_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.sdeb200_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(SolveArgs), ctypes.c_int, ctypes.c_void_p]
+        L.sdeb200_wiener_integrals.argtypes = [ctypes.c_void_p, ctypes.POINTER(WienerArgs), ctypes.c_int,
+                                               ctypes.c_void_p]
+        L.sdeb200_keys_split.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.sdeb200_normal.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+        L.sdeb200_fp64_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.sdeb200_set_device.argtypes = [ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def check(status, what=""):
+    if status == 0:
+        return
+    msg = lib().sdeb200_last_error().decode(errors="replace")
+    if status < 0:
+        raise ValueError(f"{what}: {msg}")
+    raise Sdeb200Error(f"{what}: {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise Sdeb200Error("no CUDA device available: stochastic_b200 has no CPU fallback")
+    return torch
+
+
+def current_stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------
+# compile + cache
+# ------------------------------------------------------------------------------------------
+def _core_fingerprint():
+    h = hashlib.sha256()
+    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_wiener_kernel.cuh"):
+        with open(os.path.join(CSRC_DIR, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+_FINGERPRINT = None
+_cubins = {}
+_programs = {}
+STATS = {"nvrtc_compiles": 0, "disk_hits": 0, "memory_hits": 0, "launches": 0}
+
+
+def source_key(source):
+    global _FINGERPRINT
+    if _FINGERPRINT is None:
+        _FINGERPRINT = _core_fingerprint()
+    return hashlib.sha256((_FINGERPRINT + "\n" + source).encode()).hexdigest()[:32]
+
+
+def compile_source(source, use_cache=True):
+    """CUDA text -> cubin bytes (NVRTC, sm_100a).  Cached in memory and under CACHE_DIR."""
+    key = source_key(source)
+    if use_cache and key in _cubins:
+        STATS["memory_hits"] += 1
+        return key, _cubins[key]
+    path = os.path.join(CACHE_DIR, key + ".cubin")
+    if use_cache and os.path.exists(path):
+        with open(path, "rb") as f:
+            data = f.read()
+        _cubins[key] = data
+        STATS["disk_hits"] += 1
+        return key, data
+    L = lib()
+    cubin = ctypes.c_void_p()
+    size = ctypes.c_size_t()
+    log = ctypes.c_void_p()
+    st = L.sdeb200_compile(source.encode(), CSRC_DIR.encode(), b"sm_100a", ctypes.byref(cubin), ctypes.byref(size),
+                           ctypes.byref(log))
+    if log.value:
+        L.sdeb200_free(log)
+    check(st, "NVRTC compilation of the emitted problem source failed")
+    data = ctypes.string_at(cubin.value, size.value)
+    L.sdeb200_free(cubin)
+    STATS["nvrtc_compiles"] += 1
+    _cubins[key] = data
+    if use_cache:
+        try:
+            os.makedirs(CACHE_DIR, exist_ok=True)
+            tmp = path + f".tmp{os.getpid()}"
+            with open(tmp, "wb") as f:
+                f.write(data)
+            os.replace(tmp, path)
+            with open(os.path.join(CACHE_DIR, key + ".cu"), "w") as f:
+                f.write(source)
+        except OSError:
+            pass
+    return key, data
+
+
+class Program:
+    """A cubin loaded on the current device."""
+
+    def __init__(self, key, cubin, entry):
+        self.key, self.entry = key, entry
+        self._cubin = cubin
+        self.handle = ctypes.c_void_p()
+        check(lib().sdeb200_program_load(cubin, len(cubin), entry.encode(), ctypes.byref(self.handle)),
+              "loading compiled kernel")
+
+    def info(self):
+        r, s, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(lib().sdeb200_program_info(self.handle, ctypes.byref(r), ctypes.byref(s), ctypes.byref(t)), "program_info")
+        return {"registers": r.value, "static_smem": s.value, "max_threads": t.value}
+
+
+def load_program(source, entry):
+    if os.environ.get("SDEB200_PRECOMPILE_ONLY"):
+        # cache-warming mode used on the CPU-only build box: compile, then refuse to run
+        compile_source(source)
+        raise Sdeb200Error("SDEB200_PRECOMPILE_ONLY is set: kernel compiled into the cache, not launched")
+    torch = require_cuda()
+    dev = torch.cuda.current_device()
+    key = source_key(source)
+    pk = (key, entry, dev)
+    prog = _programs.get(pk)
+    if prog is None:
+        _, cubin = compile_source(source)
+        check(lib().sdeb200_set_device(dev), "set_device")
+        prog = Program(key, cubin, entry)
+        _programs[pk] = prog
+    return prog

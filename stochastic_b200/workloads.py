@@ -1,0 +1,118 @@
+"""The BASELINE workloads as ready-made `SDEProblem`s (the "built-in functors").
+
+Each is the reference's own definition, written against `stochastic_b200.numpy`:
+
+* C1 `gbm`            reference `README.md:17`, `docs/source/examples.rst:36`
+* C2 `polar_walk`     reference `tests/test_sde_solver.py:50-63`; drifted `examples/hit.py:9-31`,
+                      `examples/examples_from_paper/polar_random_walk.py:8-16`
+* C3 `two_spheres`    reference `examples/example_two_interacting_brownian_spheres.py:12-34`
+*    `four_beads`     reference `examples/jfm.py:16-61` (spring energy selectable with / without 1/2)
+* C5 `garch`          reference `docs/source/optionpricing.rst:117-123`
+"""
+import numpy as np
+
+from . import grpy, jnp
+from .autodiff import grad
+from .sde_problem import SDEProblem
+
+
+def _finish(problem, f64):
+    if f64:
+        problem.x0 = np.asarray(problem.x0, dtype=np.float64)
+    return problem
+
+
+def gbm(alpha=0.2, beta=0.5, x0=1.0, tmax=2.0, f64=False):
+    p = SDEProblem(lambda x: alpha * x, lambda x: beta * x, x0=x0, tmax=tmax,
+                   exact_solution=lambda x0, t, w: x0 * np.exp((alpha - 0.5 * beta * beta) * t + beta * w))
+    return _finish(p, f64)
+
+
+def polar_walk(y_drift=0.0, x0=(1.0, 0.0), tmax=1.0, f64=False):
+    p = SDEProblem(
+        a=lambda x: jnp.array([1 / (2 * x[0]) + y_drift * jnp.sin(x[1]), y_drift * jnp.cos(x[1]) / x[0]]),
+        b=lambda x: jnp.array([[jnp.cos(x[1]), jnp.sin(x[1])], [-jnp.sin(x[1]) / x[0], jnp.cos(x[1]) / x[0]]]),
+        x0=jnp.array(list(x0)), tmax=tmax)
+    p.to_cartesian = lambda x: np.array([x[0] * np.cos(x[1]), x[0] * np.sin(x[1])])
+    return _finish(p, f64)
+
+
+def garch(theta=0.1, omega=0.05, xi=0.1, mu=0.01, x0=(100.0, 0.05), tmax=2.0, f64=False):
+    p = SDEProblem(lambda x: jnp.array([mu, theta * (omega - x[1])]),
+                   lambda x: jnp.array([[jnp.sqrt(x[1]) * x[0], 0], [0, xi * x[1]]]),
+                   x0=list(x0), tmax=tmax)
+    return _finish(p, f64)
+
+
+def bead_chain(radii, springs, x0, tmax, f64=False):
+    """a = mu(x) (-grad U), b = sqrt(2) chol(mu(x)), U = sum_k k_s (|r_i - r_j| - r0)^2 over `springs`
+    = [(i, j, k_s, r0), ...]; mu = RPY mobility."""
+    radii = np.asarray(radii, dtype=np.float64)
+    n = len(radii)
+
+    def u_ene(x):
+        loc = jnp.reshape(x, (n, 3))
+        e = 0.0
+        for (i, j, ks, r0) in springs:
+            e = e + ks * (jnp.sqrt(jnp.sum((loc[i] - loc[j]) ** 2)) - r0) ** 2
+        return e
+
+    def drift(x):
+        mu = grpy.muTT(jnp.reshape(x, (n, 3)), radii)
+        return jnp.matmul(mu, -grad(u_ene)(x))
+
+    def noise(x):
+        mu = grpy.muTT(jnp.reshape(x, (n, 3)), radii)
+        return jnp.sqrt(2) * jnp.linalg.cholesky(mu)
+
+    p = SDEProblem(drift, noise, x0=jnp.array(np.asarray(x0, dtype=np.float64).ravel()), tmax=tmax)
+    p.u_ene = u_ene
+    return _finish(p, f64)
+
+
+def two_spheres(tmax=500.0, f64=False):
+    return bead_chain([1.0, 0.2], [(0, 1, 1.0, 4.0)], [[0, 0, 0], [0, 0, 4.0]], tmax, f64)
+
+
+def four_beads(tmax=8000.0, half_spring=False, f64=False):
+    k = 5.5 * (0.5 if half_spring else 1.0)
+    return bead_chain([3.0, 1.0, 1.0, 1.0], [(0, 1, k, 4.0), (1, 2, k, 4.0), (2, 3, k, 4.0)],
+                      [[-2.0, 0, 0], [2.0, 0, 0], [6.0, 0, 0], [10.0, 0, 0]], tmax, f64)
+
+
+def call_payoff(strike=120.0):
+    """European call payoff max(S_T - K, 0) as a device-side observable."""
+    return lambda x, w, t: jnp.array([jnp.maximum(x[0] - strike, 0.0)])
+
+
+def polar_error_observables(y_drift=4.0, x_start=2.0):
+    """Per-trajectory strong error |cart(x_T) - (w_T + cart(x0) + drift t)| and canonical angle phi_T of the
+    drifted polar walk (cartesian motion is exact Brownian motion with drift: reference `examples/hit.py:69-80`,
+    `examples/examples_from_paper/polar_random_walk.py:30-33`)."""
+    def observables(x, w, t):
+        ex = x[0] * jnp.cos(x[1]) - (w[0] + x_start)
+        ey = x[0] * jnp.sin(x[1]) - (w[1] + y_drift * t)
+        phi = jnp.fmod(x[1] + jnp.pi, 2 * jnp.pi) - jnp.pi
+        return jnp.array([jnp.sqrt(ex * ex + ey * ey), phi])
+    return observables
+
+
+def precompile_all():
+    """NVRTC-compile (no GPU needed) the kernels of the BASELINE workloads into the cubin cache."""
+    from .sde_solver import SDESolver
+    n = 0
+    jobs = []
+    for f64 in (True, False):
+        for scheme in ("euler", "milstein", "wagner_platen"):
+            jobs.append((gbm(f64=f64), scheme, None))
+            jobs.append((polar_walk(4.0, (2.0, 0.0), f64=f64), scheme, None))
+            jobs.append((polar_walk(f64=f64), scheme, None))
+            jobs.append((garch(f64=f64), scheme, None))
+        jobs.append((two_spheres(f64=f64), "euler", None))
+        jobs.append((four_beads(f64=f64), "euler", None))
+    jobs.append((garch(f64=True), "wagner_platen", call_payoff()))
+    jobs.append((polar_walk(4.0, (2.0, 0.0), f64=True), "wagner_platen", polar_error_observables(4.0, 2.0)))
+    for prob, scheme, obs in jobs:
+        SDESolver(scheme=scheme).compile(prob, observables=obs)
+        n += 1
+    return n
