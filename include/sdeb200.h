@@ -85,12 +85,15 @@ int sdeb200_program_destroy(sdeb200_program_t* prog);
 int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, int* max_threads);
 
 /* Launch the stepping kernel: one thread per trajectory, `block` threads per CTA
- * (must equal the SDE_BLOCK the program was compiled with). */
-int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, void* stream);
+ * (must equal the SDE_BLOCK the program was compiled with), `dyn_smem_bytes` of dynamic shared
+ * memory (SDE_STAGE_COUNT * SDE_BLOCK * sizeof(real): the per-thread staging columns of the
+ * in-kernel normal generator). */
+int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block,
+                  size_t dyn_smem_bytes, void* stream);
 
 /* Launch the unit-step Wiener-integral generator kernel (one thread per step). */
 int sdeb200_wiener_integrals(sdeb200_program_t* prog, const sdeb200_wiener_args_t* args, int block,
-                             void* stream);
+                             size_t dyn_smem_bytes, void* stream);
 
 /* jax.random.split(PRNGKey(seed), n_total)[begin : begin+count] -> device uint32 (count, 2).
  * layout 0 = original (jax<0.5), 1 = partitionable.  pychastic/sde_solver.py:299. */

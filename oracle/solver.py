@@ -49,15 +49,19 @@ class OracleProblem:
 
 
 def _autodiff_coeffs(problem, scheme, dtype):
+    # Coefficient tensors are always evaluated in float64 and rounded to the working dtype: nested
+    # torch.func.jacfwd mixes dtypes in float32, and a correctly rounded coefficient is within half an ulp
+    # of whatever float32 evaluation order the reference's XLA program would use.
     fns = batched_coefficient_functions(problem.a, problem.b)
-    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    tdt = torch.float64
+    out_dt = np.dtype(dtype)
     need = {"euler": ("f_t", "f_w"),
             "milstein": ("f_t", "f_w", "f_ww"),
             "wagner_platen": ("f_t", "f_w", "f_ww", "f_tw", "f_wt", "f_www", "f_tt")}[scheme]
 
     def coeffs(x):
         xt = torch.as_tensor(x, dtype=tdt)
-        return {k: fns[k](xt).numpy() for k in need}
+        return {k: fns[k](xt).numpy().astype(out_dt) for k in need}
     return coeffs
 
 

@@ -35,6 +35,7 @@ typedef float real;
 #define RC(x) x##f
 #endif
 
+#define SDE_PI 3.14159265358979323846
 #define SDE_EULER 0
 #define SDE_MILSTEIN 1
 #define SDE_WAGNER_PLATEN 2
@@ -121,103 +122,113 @@ __device__ __forceinline__ u32 random_bits32(Key key, u32 e, u32 size) {
 // ----------------------------------------------------------------------------------------
 // erf_inv: XLA's expansion (Giles' polynomials), w = -log1p(-x*x)
 // ----------------------------------------------------------------------------------------
+// Coefficients live in constant memory: each Horner step is then ONE FMA with a c[bank][offset]
+// operand instead of two immediate moves + FMA, and the unrolled polynomial stays small.
+static __constant__ float ERFINV32_LT5[9] = {2.81022636e-08f, 3.43273939e-07f, -3.5233877e-06f, -4.39150654e-06f,
+                                      0.00021858087f,  -0.00125372503f, -0.00417768164f, 0.246640727f,
+                                      1.50140941f};
+static __constant__ float ERFINV32_GE5[9] = {-0.000200214257f, 0.000100950558f, 0.00134934322f, -0.00367342844f,
+                                      0.00573950773f,   -0.0076224613f,  0.00943887047f, 1.00167406f,
+                                      2.83297682f};
+static __constant__ double ERFINV64_LT6_25[23] = {
+    -3.6444120640178196996e-21, -1.685059138182016589e-19,  1.2858480715256400167e-18, 1.115787767802518096e-17,
+    -1.333171662854620906e-16,  2.0972767875968561637e-17,  6.6376381343583238325e-15, -4.0545662729752068639e-14,
+    -8.1519341976054721522e-14, 2.6335093153082322977e-12,  -1.2975133253453532498e-11, -5.4154120542946279317e-11,
+    1.051212273321532285e-09,   -4.1126339803469836976e-09, -2.9070369957882005086e-08, 4.2347877827932403518e-07,
+    -1.3654692000834678645e-06, -1.3882523362786468719e-05, 0.0001867342080340571352,  -0.00074070253416626697512,
+    -0.0060336708714301490533,  0.24015818242558961693,     1.6536545626831027356};
+static __constant__ double ERFINV64_LT16[19] = {
+    2.2137376921775787049e-09,  9.0756561938885390979e-08,  -2.7517406297064545428e-07, 1.8239629214389227755e-08,
+    1.5027403968909827627e-06,  -4.013867526981545969e-06,  2.9234449089955446044e-06,  1.2475304481671778723e-05,
+    -4.7318229009055733981e-05, 6.8284851459573175448e-05,  2.4031110387097893999e-05,  -0.0003550375203628474796,
+    0.00095328937973738049703,  -0.0016882755560235047313,  0.0024914420961078508066,   -0.0037512085075692412107,
+    0.005370914553590063617,    1.0052589676941592334,      3.0838856104922207635};
+static __constant__ double ERFINV64_GE16[17] = {
+    -2.7109920616438573243e-11, -2.5556418169965252055e-10, 1.5076572693500548083e-09,  -3.7894654401267369937e-09,
+    7.6157012080783393804e-09,  -1.4960026627149240478e-08, 2.9147953450901080826e-08,  -6.7711997758452339498e-08,
+    2.2900482228026654717e-07,  -9.9298272942317002539e-07, 4.5260625972231537039e-06,  -1.9681778105531670567e-05,
+    7.5995277030017761139e-05,  -0.00021503011930044477347, -0.00013871931833623122026, 1.0103004648645343977,
+    4.8499064014085844221};
+
 __device__ __forceinline__ float erfinv_xla(float x) {
     float w = -log1pf(-x * x);
     float p;
     if (w < 5.0f) {
         w = w - 2.5f;
-        p = 2.81022636e-08f;
-        p = fmaf(p, w, 3.43273939e-07f);
-        p = fmaf(p, w, -3.5233877e-06f);
-        p = fmaf(p, w, -4.39150654e-06f);
-        p = fmaf(p, w, 0.00021858087f);
-        p = fmaf(p, w, -0.00125372503f);
-        p = fmaf(p, w, -0.00417768164f);
-        p = fmaf(p, w, 0.246640727f);
-        p = fmaf(p, w, 1.50140941f);
+        p = ERFINV32_LT5[0];
+#pragma unroll
+        for (int i = 1; i < 9; ++i) p = fmaf(p, w, ERFINV32_LT5[i]);
     } else {
         w = sqrtf(w) - 3.0f;
-        p = -0.000200214257f;
-        p = fmaf(p, w, 0.000100950558f);
-        p = fmaf(p, w, 0.00134934322f);
-        p = fmaf(p, w, -0.00367342844f);
-        p = fmaf(p, w, 0.00573950773f);
-        p = fmaf(p, w, -0.0076224613f);
-        p = fmaf(p, w, 0.00943887047f);
-        p = fmaf(p, w, 1.00167406f);
-        p = fmaf(p, w, 2.83297682f);
+        p = ERFINV32_GE5[0];
+#pragma unroll
+        for (int i = 1; i < 9; ++i) p = fmaf(p, w, ERFINV32_GE5[i]);
     }
     return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7f800000) : p * x;
 }
 
+// Lg1..Lg7 of fdlibm's e_log.c, then ln2_hi, ln2_lo
+static __constant__ double LOGC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                      2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                      1.479819860511658591e-01, 6.93147180369123816490e-01,
+                                      1.90821492927058770002e-10};
+
+// w = -log(1 - x^2) = -log1p(-x*x) for |x| < 1, branch-free.
+//
+// CUDA's log1p() takes one of two ~110-instruction paths depending on the argument, and the lanes of
+// a warp split evenly between them, so every normal paid for both.  Here t = 1 - x^2 is reduced to m in [sqrt(1/2), sqrt(2)) with integer ops on the exponent field, and
+// log(m) is evaluated with the classic s = f/(2+f) series (fdlibm's e_log.c scheme and its published
+// minimax coefficients Lg1..Lg7, |error| < 2^-58 on the reduced interval).  s only enters through a
+// second-order term, so an approximate reciprocal refined by two Newton steps replaces the division.
+// Absolute error of w is ~1e-16 (1 + w): indistinguishable from log1p's own last-place error.
+__device__ __forceinline__ double neg_log_one_minus_sq(double x) {
+    // x*x is rounded BEFORE the subtraction, exactly as in XLA's `-log1p(-x * x)`: near |x| = 1 the
+    // result is ill-conditioned in x*x, so a fused 1 - x*x would change the far-tail normals.
+    const double t = 1.0 - __dmul_rn(x, x);                 // in (0, 1], always a normal number
+    int hi = __double2hiint(t);
+    const int lo = __double2loint(t);
+    hi += 0x3ff00000 - 0x3fe6a09e;                          // shift the split point to sqrt(2)/2
+    const int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) + 0x3fe6a09e;
+    const double f = __hiloint2double(hi, lo) - 1.0;        // m - 1, m in [sqrt(1/2), sqrt(2))
+    const double d = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    const double s = f * r;
+    const double z = s * s;
+    const double z2 = z * z;
+    const double t1 = z2 * fma(z2, fma(z2, LOGC[5], LOGC[3]), LOGC[1]);
+    const double t2 = z * fma(z2, fma(z2, fma(z2, LOGC[6], LOGC[4]), LOGC[2]), LOGC[0]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    // log(t) = k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f);  w = -log(t)
+    const double inner = (hfsq - fma(s, hfsq + R, dk * LOGC[8])) - f;
+    return fma(-dk, LOGC[7], inner);
+}
+
 __device__ __forceinline__ double erfinv_xla(double x) {
-    double w = -log1p(-x * x);
+    double w = neg_log_one_minus_sq(x);
     double p;
     if (w < 6.25) {
         w = w - 3.125;
-        p = -3.6444120640178196996e-21;
-        p = fma(p, w, -1.685059138182016589e-19);
-        p = fma(p, w, 1.2858480715256400167e-18);
-        p = fma(p, w, 1.115787767802518096e-17);
-        p = fma(p, w, -1.333171662854620906e-16);
-        p = fma(p, w, 2.0972767875968561637e-17);
-        p = fma(p, w, 6.6376381343583238325e-15);
-        p = fma(p, w, -4.0545662729752068639e-14);
-        p = fma(p, w, -8.1519341976054721522e-14);
-        p = fma(p, w, 2.6335093153082322977e-12);
-        p = fma(p, w, -1.2975133253453532498e-11);
-        p = fma(p, w, -5.4154120542946279317e-11);
-        p = fma(p, w, 1.051212273321532285e-09);
-        p = fma(p, w, -4.1126339803469836976e-09);
-        p = fma(p, w, -2.9070369957882005086e-08);
-        p = fma(p, w, 4.2347877827932403518e-07);
-        p = fma(p, w, -1.3654692000834678645e-06);
-        p = fma(p, w, -1.3882523362786468719e-05);
-        p = fma(p, w, 0.0001867342080340571352);
-        p = fma(p, w, -0.00074070253416626697512);
-        p = fma(p, w, -0.0060336708714301490533);
-        p = fma(p, w, 0.24015818242558961693);
-        p = fma(p, w, 1.6536545626831027356);
+        p = ERFINV64_LT6_25[0];
+#pragma unroll
+        for (int i = 1; i < 23; ++i) p = fma(p, w, ERFINV64_LT6_25[i]);
     } else if (w < 16.0) {
         w = sqrt(w) - 3.25;
-        p = 2.2137376921775787049e-09;
-        p = fma(p, w, 9.0756561938885390979e-08);
-        p = fma(p, w, -2.7517406297064545428e-07);
-        p = fma(p, w, 1.8239629214389227755e-08);
-        p = fma(p, w, 1.5027403968909827627e-06);
-        p = fma(p, w, -4.013867526981545969e-06);
-        p = fma(p, w, 2.9234449089955446044e-06);
-        p = fma(p, w, 1.2475304481671778723e-05);
-        p = fma(p, w, -4.7318229009055733981e-05);
-        p = fma(p, w, 6.8284851459573175448e-05);
-        p = fma(p, w, 2.4031110387097893999e-05);
-        p = fma(p, w, -0.0003550375203628474796);
-        p = fma(p, w, 0.00095328937973738049703);
-        p = fma(p, w, -0.0016882755560235047313);
-        p = fma(p, w, 0.0024914420961078508066);
-        p = fma(p, w, -0.0037512085075692412107);
-        p = fma(p, w, 0.005370914553590063617);
-        p = fma(p, w, 1.0052589676941592334);
-        p = fma(p, w, 3.0838856104922207635);
+        p = ERFINV64_LT16[0];
+#pragma unroll 1
+        for (int i = 1; i < 19; ++i) p = fma(p, w, ERFINV64_LT16[i]);
     } else {
         w = sqrt(w) - 5.0;
-        p = -2.7109920616438573243e-11;
-        p = fma(p, w, -2.5556418169965252055e-10);
-        p = fma(p, w, 1.5076572693500548083e-09);
-        p = fma(p, w, -3.7894654401267369937e-09);
-        p = fma(p, w, 7.6157012080783393804e-09);
-        p = fma(p, w, -1.4960026627149240478e-08);
-        p = fma(p, w, 2.9147953450901080826e-08);
-        p = fma(p, w, -6.7711997758452339498e-08);
-        p = fma(p, w, 2.2900482228026654717e-07);
-        p = fma(p, w, -9.9298272942317002539e-07);
-        p = fma(p, w, 4.5260625972231537039e-06);
-        p = fma(p, w, -1.9681778105531670567e-05);
-        p = fma(p, w, 7.5995277030017761139e-05);
-        p = fma(p, w, -0.00021503011930044477347);
-        p = fma(p, w, -0.00013871931833623122026);
-        p = fma(p, w, 1.0103004648645343977);
-        p = fma(p, w, 4.8499064014085844221);
+        p = ERFINV64_GE16[0];
+#pragma unroll 1
+        for (int i = 1; i < 17; ++i) p = fma(p, w, ERFINV64_GE16[i]);
     }
     return (fabs(x) == 1.0) ? x * __longlong_as_double(0x7ff0000000000000LL) : p * x;
 }
@@ -267,6 +278,23 @@ struct StepScale {
     real dt;
     real dt32;      // dt**1.5 computed in double on the host, cast
 };
+
+// Number of normals per step that are produced by a ROLLED loop and staged through this thread's
+// column of shared memory before being read back with compile-time indices.  Keeping the
+// normal generator (threefry + log1p + 23-term Horner) out of the unrolled code is what keeps the
+// step body inside the instruction cache.
+#if SDE_M > 1 && SDE_SCHEME == SDE_WAGNER_PLATEN
+#define SDE_STAGE_COUNT (2 * SDE_M * SDE_P + 3 * SDE_M)
+#elif SDE_M > 4 && SDE_SCHEME == SDE_EULER
+#define SDE_STAGE_COUNT (SDE_M)
+#else
+#define SDE_STAGE_COUNT 0
+#endif
+#ifndef SDE_BLOCK
+#define SDE_BLOCK 128
+#endif
+// element k of this thread's staging column (stage points at the thread's slot of row 0)
+#define SDE_STAGE(k) stage[(k) * SDE_BLOCK]
 
 // compile-time helpers ---------------------------------------------------------------------
 #if SDE_P <= 16
@@ -334,7 +362,7 @@ struct WienerGen {
 #endif
     }
 
-    __device__ __forceinline__ void generate(u32 s, const StepScale& sc, Integrals& I) const {
+    __device__ __forceinline__ void generate(u32 s, const StepScale& sc, Integrals& I, real* stage) const {
 #if SDE_M == 1
         // closed forms, reference vectorized_I_generation.py:265-294
 #if SDE_SCHEME == SDE_WAGNER_PLATEN
@@ -354,13 +382,21 @@ struct WienerGen {
 #endif
 #endif
 #elif SDE_SCHEME == SDE_EULER
+#if SDE_STAGE_COUNT > 0
+#pragma unroll 1
+        for (int j = 0; j < SDE_M; ++j) SDE_STAGE(j) = normal_elem(k0, s * SDE_M + j, S * SDE_M);
+#pragma unroll
+        for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * SDE_STAGE(j);
+#else
 #pragma unroll
         for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * normal_elem(k0, s * SDE_M + j, S * SDE_M);
+#endif
 #elif SDE_SCHEME == SDE_MILSTEIN
         gen_milstein(s, sc, I);
 #else
-        gen_wagner_platen(s, sc, I);
+        gen_wagner_platen(s, sc, I, stage);
 #endif
+        (void)stage;
     }
 
 #if SDE_M > 1 && SDE_SCHEME == SDE_MILSTEIN
@@ -378,7 +414,7 @@ struct WienerGen {
         for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int j = 0; j < M; ++j) ser[i][j] = RC(0.0);
-        SDE_UNROLL
+#pragma unroll 1
         for (int r = 1; r <= P; ++r) {
             real a[M], z[M];
 #pragma unroll
@@ -396,7 +432,7 @@ struct WienerGen {
         real rho = RC(0.0);
         SDE_UNROLL
         for (int r = 1; r <= P; ++r) rho += RC(1.0) / (real)(r * r);
-        rho = RC(0.083333333333333333333) - rho * RC(0.050660591821168885722);  // 1/12 - sum/(2 pi^2)
+        rho = RC(0.083333333333333333333) - rho * (real)(0.5 / (SDE_PI * SDE_PI));  // 1/12 - sum/(2 pi^2)
         const real sqrt_rho = sqrt(rho);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
@@ -406,7 +442,7 @@ struct WienerGen {
             for (int j = i + 1; j < M; ++j) {
                 const real sym = RC(0.5) * xi[i] * xi[j];
                 const real asym = sqrt_rho * (xi[i] * mu[j] - mu[i] * xi[j]) +
-                                  RC(0.15915494309189533577) * ser[i][j];
+                                  (real)(0.5 / SDE_PI) * ser[i][j];
                 I.Iww[i][j] = sc.dt * (sym + asym);
                 I.Iww[j][i] = sc.dt * (sym - asym);
             }
@@ -419,9 +455,37 @@ struct WienerGen {
     // Works on the prescaled series coefficients zs[j][r] = zeta_{r,j}/r, es[j][r] = eta_{r,j}/r,
     // which turns every term of the C and D double sums into a single FMA, and shares the
     // correlation / convolution partial sums between D[j1,.,j3] and D[j3,.,j1].
-    __device__ __forceinline__ void gen_wagner_platen(u32 s, const StepScale& sc, Integrals& I) const {
+    __device__ __forceinline__ void gen_wagner_platen(u32 s, const StepScale& sc, Integrals& I, real* stage) const {
         constexpr int M = SDE_M, P = SDE_P;
-        const real PI = RC(3.14159265358979323846);
+        // -- normals: rolled loops into the staging column -------------------------------------
+        // 2M independent normals per iteration: enough instruction-level parallelism to cover the
+        // dependent threefry rounds / Horner chains with only two resident warps per scheduler.
+        {
+            const u32 base = s * (u32)(P * M), size = S * (u32)(P * M);
+#pragma unroll 1
+            for (int r = 0; r < P; ++r) {
+                real z[M], h[M];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    z[j] = normal_elem(k_zeta, base + r * M + j, size);
+                    h[j] = normal_elem(k_eta, base + r * M + j, size);
+                }
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    SDE_STAGE(r * M + j) = z[j];
+                    SDE_STAGE(P * M + r * M + j) = h[j];
+                }
+            }
+#pragma unroll 1
+            for (int j = 0; j < M; ++j) {
+                const real n0 = normal_elem(k_xi, s * M + j, S * M);
+                const real n1 = normal_elem(k_mu, s * M + j, S * M);
+                const real n2 = normal_elem(k_phi, s * M + j, S * M);
+                SDE_STAGE(2 * P * M + j) = n0;
+                SDE_STAGE(2 * P * M + M + j) = n1;
+                SDE_STAGE(2 * P * M + 2 * M + j) = n2;
+            }
+        }
         real xi[M], a[M], b[M];
         real zs[M][P + 1], es[M][P + 1];
         {
@@ -433,9 +497,8 @@ struct WienerGen {
                 const real rec = RC(1.0) / (real)r;
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                    const u32 e = (s * P + (r - 1)) * M + j;
-                    const real z = rec * normal_elem(k_zeta, e, S * P * M);
-                    const real h = rec * normal_elem(k_eta, e, S * P * M);
+                    const real z = rec * SDE_STAGE((r - 1) * M + j);
+                    const real h = rec * SDE_STAGE(P * M + (r - 1) * M + j);
                     zs[j][r] = z;
                     es[j][r] = h;
                     sa[j] += z;                       // sum zeta_r / r
@@ -449,16 +512,16 @@ struct WienerGen {
                 rho += r2;
                 alpha += r2 * r2;
             }
-            rho = RC(0.083333333333333333333) - rho * RC(0.050660591821168885722);      // 1/12 - sum/(2 pi^2)
-            alpha = RC(0.054831135561607547882) - alpha * RC(0.050660591821168885722);  // pi^2/180 - sum/(2 pi^2)
+            rho = RC(0.083333333333333333333) - rho * (real)(0.5 / (SDE_PI * SDE_PI));      // 1/12 - sum/(2 pi^2)
+            alpha = (real)(SDE_PI * SDE_PI / 180.0) - alpha * (real)(0.5 / (SDE_PI * SDE_PI));  // pi^2/180 - sum/(2 pi^2)
             const real two_sqrt_rho = RC(2.0) * sqrt(rho), sqrt_alpha = sqrt(alpha);
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                xi[j] = normal_elem(k_xi, s * M + j, S * M);
-                const real mu = normal_elem(k_mu, s * M + j, S * M);
-                const real phi = normal_elem(k_phi, s * M + j, S * M);
-                a[j] = -RC(0.45015815807855303478) * sa[j] - two_sqrt_rho * mu;   // sqrt(2)/pi
-                b[j] = fma(RC(0.22507907903927651739), sb[j], sqrt_alpha * phi);  // 1/(sqrt(2) pi)
+                xi[j] = SDE_STAGE(2 * P * M + j);
+                const real mu = SDE_STAGE(2 * P * M + M + j);
+                const real phi = SDE_STAGE(2 * P * M + 2 * M + j);
+                a[j] = -(real)(1.4142135623730950488 / SDE_PI) * sa[j] - two_sqrt_rho * mu;   // sqrt(2)/pi
+                b[j] = fma((real)(1.0 / (1.4142135623730950488 * SDE_PI)), sb[j], sqrt_alpha * phi);  // 1/(sqrt(2) pi)
             }
         }
 
@@ -475,8 +538,8 @@ struct WienerGen {
                     sB = fma(es[i][r], es[j][r], sB);
                     if (j > i) sA = fma((real)r * zs[i][r], es[j][r], fma(-(real)r * es[i][r], zs[j][r], sA));
                 }
-                B[i][j] = B[j][i] = RC(0.025330295910584442861) * sB;     // 1/(4 pi^2)
-                A[i][j] = RC(0.15915494309189533577) * sA;                // 1/(2 pi)
+                B[i][j] = B[j][i] = (real)(0.25 / (SDE_PI * SDE_PI)) * sB;     // 1/(4 pi^2)
+                A[i][j] = (real)(0.5 / SDE_PI) * sA;                // 1/(2 pi)
                 A[j][i] = -A[i][j];
             }
         }
@@ -504,14 +567,14 @@ struct WienerGen {
                 real c = RC(0.0);
                 SDE_UNROLL
                 for (int l = 1; l <= P; ++l) c = fma(zs[j2][l], Uz[l], fma(es[j2][l], Ue[l], c));
-                C[j1][j2] = -RC(0.050660591821168885722) * c;
+                C[j1][j2] = -(real)(0.5 / (SDE_PI * SDE_PI)) * c;
             }
         }
 
         // D[j1][j2][j3] = K sum_l ( zs[j2][l] Tz_{j1 j3}[l] + es[j2][l] Te_{j1 j3}[l] ), the factor l
         // that undoes the prescaling of the j2 coefficient is folded into Tz / Te.
         real D[M][M][M];
-        const real KD = RC(0.017911224018155010247);  // 1 / (pi^2 2^(5/2))
+        const real KD = (real)(1.0 / (SDE_PI * SDE_PI * 5.6568542494923801952));  // 1 / (pi^2 2^(5/2))
 #pragma unroll
         for (int ja = 0; ja < M; ++ja) {
             {   // j1 = j3 = ja:  Tz = 2 (corr_ze - corr_ez + conv_ze),  Te = conv_ee - conv_zz
@@ -614,7 +677,7 @@ struct WienerGen {
             I.Itw[j] = sc.dt32 * tw[j];
         }
         real Jww[M][M], Jtww[M][M];
-        const real inv_pi = RC(0.31830988618379067154);
+        const real inv_pi = (real)(1.0 / SDE_PI);
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -639,7 +702,6 @@ struct WienerGen {
                     if (j == k) J -= RC(0.5) * wt[i];
                     I.Iwww[i][j][k] = sc.dt32 * J;
                 }
-        (void)PI;
     }
 #endif
 };

@@ -10,9 +10,10 @@
 #define SDE_CAT2(a, b) a##b
 #define SDE_CAT(a, b) SDE_CAT2(a, b)
 
-namespace {
+#define KEYS_KERNEL SDE_CAT(keys_split_kernel_, SDE_SUFFIX)
+#define NORMAL_KERNEL SDE_CAT(normal_kernel_, SDE_SUFFIX)
 
-__global__ void keys_split_kernel(sdeb::Key root, u64 n_total, u64 begin, u64 count, u32* out) {
+__global__ void KEYS_KERNEL(sdeb::Key root, u64 n_total, u64 begin, u64 count, u32* out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const sdeb::Key k = sdeb::split_key(root, n_total, begin + i);
@@ -20,13 +21,11 @@ __global__ void keys_split_kernel(sdeb::Key root, u64 n_total, u64 begin, u64 co
     out[2 * i + 1] = k.b;
 }
 
-__global__ void normal_kernel(sdeb::Key key, u64 n, real* out) {
+__global__ void NORMAL_KERNEL(sdeb::Key key, u64 n, real* out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = sdeb::normal_elem(key, (u32)i, (u32)n);
 }
-
-}  // namespace
 
 extern "C" int SDE_CAT(sdeb200_keys_split_, SDE_SUFFIX)(u32 ka, u32 kb, u64 n_total, u64 begin, u64 count, u32* out,
                                                       void* stream) {
@@ -34,7 +33,7 @@ extern "C" int SDE_CAT(sdeb200_keys_split_, SDE_SUFFIX)(u32 ka, u32 kb, u64 n_to
     k.a = ka;
     k.b = kb;
     const unsigned grid = (unsigned)((count + 255) / 256);
-    keys_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, n_total, begin, count, out);
+    KEYS_KERNEL<<<grid, 256, 0, (cudaStream_t)stream>>>(k, n_total, begin, count, out);
     return (int)cudaGetLastError();
 }
 
@@ -43,6 +42,6 @@ extern "C" int SDE_CAT(sdeb200_normal_, SDE_SUFFIX)(u32 ka, u32 kb, u64 n, void*
     k.a = ka;
     k.b = kb;
     const unsigned grid = (unsigned)((n + 255) / 256);
-    normal_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, n, (real*)out);
+    NORMAL_KERNEL<<<grid, 256, 0, (cudaStream_t)stream>>>(k, n, (real*)out);
     return (int)cudaGetLastError();
 }

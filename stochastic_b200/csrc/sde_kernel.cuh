@@ -11,14 +11,17 @@
 //   __device__ void sde_observe(const real*, const real*, real, double (&obs)[SDE_NOBS]);  // if SDE_NOBS > 0
 #pragma once
 
-#ifndef SDE_BLOCK
-#define SDE_BLOCK 128
-#endif
 #ifndef SDE_NOBS
 #define SDE_NOBS 0
 #endif
 #ifndef SDE_HAS_POST
 #define SDE_HAS_POST 0
+#endif
+#ifndef SDE_MIN_BLOCKS
+#define SDE_MIN_BLOCKS 1
+#endif
+#ifndef SDE_LOCKSTEP
+#define SDE_LOCKSTEP (SDE_STAGE_COUNT > 0)
 #endif
 
 namespace sdeb {
@@ -46,18 +49,23 @@ struct SolveArgs {
 
 }  // namespace sdeb
 
-extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_solve_kernel(const sdeb::SolveArgs A) {
+// dynamic shared memory: SDE_STAGE_COUNT rows of SDE_BLOCK reals (the normals staging area)
+extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solve_kernel(const sdeb::SolveArgs A) {
     using namespace sdeb;
-    const u64 tid = (u64)blockIdx.x * SDE_BLOCK + threadIdx.x;
-    const bool active = tid < A.traj_count;
+    real* const stage = reinterpret_cast<real*>(sde_dyn_smem) + threadIdx.x;
+    const u64 tid_raw = (u64)blockIdx.x * SDE_BLOCK + threadIdx.x;
+    const bool active = tid_raw < A.traj_count;
+    // Threads past the end integrate trajectory 0 again (no stores): every thread of the CTA then runs the
+    // same number of steps, which the per-step barrier below relies on.
+    const u64 tid = active ? tid_raw : 0;
 #if SDE_NOBS > 0
     double obs[SDE_NOBS];
 #pragma unroll
     for (int k = 0; k < SDE_NOBS; ++k) obs[k] = 0.0;
-#else
-    if (!active) return;
 #endif
-    if (active) {
+    {
         Key root;
         root.a = A.key_a;
         root.b = A.key_b;
@@ -82,8 +90,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_solve_kernel(const s
             u32 s = 0;
             for (u32 c = 0; c < A.cpr && snap < A.n_snapshots; ++c, ++snap) {
                 for (u32 k = 0; k < A.chunk; ++k, ++s) {
+#if SDE_LOCKSTEP
+                    // Keep the warps of the CTA on the same stretch of the (large, mostly straight-line) step
+                    // body so that one instruction-cache fill serves all of them.
+                    __syncthreads();
+#endif
                     Integrals I;
-                    gen.generate(s, sc, I);
+                    gen.generate(s, sc, I, stage);
                     t += sc.dt;
                     sde_step(x, I, sc.dt);
 #if SDE_HAS_POST
@@ -93,6 +106,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_solve_kernel(const s
                     for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
                 }
                 const u64 row = tid * (u64)A.n_snapshots + snap;
+                if (!active) continue;
                 if (A.out_t) A.out_t[row] = t;
                 if (A.out_x) {
 #pragma unroll

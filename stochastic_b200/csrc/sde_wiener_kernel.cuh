@@ -18,9 +18,12 @@ struct WienerArgs {
 };
 }  // namespace sdeb
 
-extern "C" __global__ void __launch_bounds__(128) sde_wiener_kernel(const sdeb::WienerArgs A) {
+extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_wiener_kernel(const sdeb::WienerArgs A) {
     using namespace sdeb;
-    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    real* const stage = reinterpret_cast<real*>(sde_dyn_smem) + threadIdx.x;
+    const u32 s = blockIdx.x * SDE_BLOCK + threadIdx.x;
     if (s >= A.steps) return;
     Key key;
     key.a = A.key_a;
@@ -32,7 +35,7 @@ extern "C" __global__ void __launch_bounds__(128) sde_wiener_kernel(const sdeb::
     sc.sqrt_dt = RC(1.0);
     sc.dt32 = RC(1.0);
     Integrals I;
-    gen.generate(s, sc, I);
+    gen.generate(s, sc, I, stage);
     constexpr int M = SDE_M;
 #pragma unroll
     for (int j = 0; j < M; ++j) A.d_w[(u64)s * M + j] = I.dW[j];

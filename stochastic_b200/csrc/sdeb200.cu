@@ -42,6 +42,7 @@ struct Driver {
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              CUstream, void**, void**) = nullptr;
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
     bool ok = false;
     std::string why;
@@ -67,6 +68,7 @@ Driver& driver() {
         BIND(ModuleGetFunction, "cuModuleGetFunction")
         BIND(LaunchKernel, "cuLaunchKernel")
         BIND(FuncGetAttribute, "cuFuncGetAttribute")
+        BIND(FuncSetAttribute, "cuFuncSetAttribute")
         BIND(GetErrorString, "cuGetErrorString")
 #undef BIND
         d.ok = true;
@@ -85,7 +87,19 @@ std::string cu_err(CUresult r) {
 struct sdeb200_program {
     CUmodule module = nullptr;
     CUfunction func = nullptr;
+    size_t smem_optin = 0;  // largest dynamic shared memory size already opted in for
 };
+
+namespace {
+int ensure_smem(sdeb200_program* p, size_t bytes) {
+    if (bytes <= 48 * 1024 || bytes <= p->smem_optin) return 0;
+    if (bytes > 227 * 1024) return fail(-1, "dynamic shared memory request exceeds 227 KB");
+    CUresult r = driver().FuncSetAttribute(p->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)bytes);
+    if (r != CUDA_SUCCESS) return fail(3, "cuFuncSetAttribute(max dynamic smem): " + cu_err(r));
+    p->smem_optin = bytes;
+    return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -186,7 +200,8 @@ int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, in
     return 0;
 }
 
-int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, void* stream) {
+int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, size_t dyn_smem_bytes,
+                  void* stream) {
     if (!prog || !args) return fail(-1, "sdeb200_solve: null argument");
     if (block <= 0 || block > 1024 || (block % 32)) return fail(-1, "sdeb200_solve: bad block size");
     if (args->traj_count == 0) return 0;
@@ -200,24 +215,26 @@ int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int
     if (!(args->dt > 0)) return fail(-1, "sdeb200_solve: dt must be positive");
     uint64_t grid = (args->traj_count + (uint64_t)block - 1) / (uint64_t)block;
     if (grid > 0x7fffffffULL) return fail(-1, "sdeb200_solve: too many trajectories for one launch");
+    if (int e = ensure_smem(prog, dyn_smem_bytes)) return e;
     sdeb200_solve_args_t a = *args;
     void* params[] = {&a};
-    CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0,
-                                       (CUstream)stream, params, nullptr);
+    CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1,
+                                       (unsigned)dyn_smem_bytes, (CUstream)stream, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_solve_kernel): " + cu_err(r));
     return 0;
 }
 
 int sdeb200_wiener_integrals(sdeb200_program_t* prog, const sdeb200_wiener_args_t* args, int block,
-                             void* stream) {
+                             size_t dyn_smem_bytes, void* stream) {
     if (!prog || !args) return fail(-1, "sdeb200_wiener_integrals: null argument");
     if (args->steps == 0) return 0;
     if (!args->d_w) return fail(-1, "sdeb200_wiener_integrals: d_w is NULL");
     unsigned grid = (args->steps + (unsigned)block - 1) / (unsigned)block;
+    if (int e = ensure_smem(prog, dyn_smem_bytes)) return e;
     sdeb200_wiener_args_t a = *args;
     void* params[] = {&a};
-    CUresult r = driver().LaunchKernel(prog->func, grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream,
-                                       params, nullptr);
+    CUresult r = driver().LaunchKernel(prog->func, grid, 1, 1, (unsigned)block, 1, 1, (unsigned)dyn_smem_bytes,
+                                       (CUstream)stream, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_wiener_kernel): " + cu_err(r));
     return 0;
 }

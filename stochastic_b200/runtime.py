@@ -79,9 +79,10 @@ def lib():
         L.sdeb200_program_destroy.argtypes = [ctypes.c_void_p]
         L.sdeb200_program_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
-        L.sdeb200_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(SolveArgs), ctypes.c_int, ctypes.c_void_p]
+        L.sdeb200_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(SolveArgs), ctypes.c_int, ctypes.c_size_t,
+                                    ctypes.c_void_p]
         L.sdeb200_wiener_integrals.argtypes = [ctypes.c_void_p, ctypes.POINTER(WienerArgs), ctypes.c_int,
-                                               ctypes.c_void_p]
+                                               ctypes.c_size_t, ctypes.c_void_p]
         L.sdeb200_keys_split.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.sdeb200_normal.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
@@ -90,6 +91,26 @@ def lib():
         L.sdeb200_set_device.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
+
+
+def stage_count(m, p, scheme):
+    """Normals per step staged through shared memory; must equal SDE_STAGE_COUNT in csrc/sde_core.cuh
+    (the emitted sources carry a static_assert)."""
+    if m > 1 and scheme == "wagner_platen":
+        return 2 * m * p + 3 * m
+    if m > 4 and scheme == "euler":
+        return m
+    return 0
+
+
+def pick_block(m, p, scheme, f64, preferred=None):
+    """CTA size.  Kernels with a staged normal generator (large step bodies) use one 256-thread CTA per SM whose
+    warps are kept in lock-step by a per-step barrier; the staging area must fit in 200 KB of shared memory."""
+    stage = stage_count(m, p, scheme)
+    block = preferred or (256 if stage else 128)
+    while block > 32 and stage * block * (8 if f64 else 4) > 200 * 1024:
+        block //= 2
+    return block
 
 
 def check(status, what=""):

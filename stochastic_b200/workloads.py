@@ -16,16 +16,18 @@ from .autodiff import grad
 from .sde_problem import SDEProblem
 
 
-def _finish(problem, f64):
+def _finish(problem, f64, x0=None):
+    """fp64 runs: overwrite x0 with the exact double values (SDEProblem stores float32 like the reference)."""
     if f64:
-        problem.x0 = np.asarray(problem.x0, dtype=np.float64)
+        src = problem.x0 if x0 is None else np.asarray(x0, dtype=np.float64).reshape(np.shape(problem.x0))
+        problem.x0 = np.asarray(src, dtype=np.float64)
     return problem
 
 
 def gbm(alpha=0.2, beta=0.5, x0=1.0, tmax=2.0, f64=False):
     p = SDEProblem(lambda x: alpha * x, lambda x: beta * x, x0=x0, tmax=tmax,
                    exact_solution=lambda x0, t, w: x0 * np.exp((alpha - 0.5 * beta * beta) * t + beta * w))
-    return _finish(p, f64)
+    return _finish(p, f64, x0)
 
 
 def polar_walk(y_drift=0.0, x0=(1.0, 0.0), tmax=1.0, f64=False):
@@ -34,14 +36,14 @@ def polar_walk(y_drift=0.0, x0=(1.0, 0.0), tmax=1.0, f64=False):
         b=lambda x: jnp.array([[jnp.cos(x[1]), jnp.sin(x[1])], [-jnp.sin(x[1]) / x[0], jnp.cos(x[1]) / x[0]]]),
         x0=jnp.array(list(x0)), tmax=tmax)
     p.to_cartesian = lambda x: np.array([x[0] * np.cos(x[1]), x[0] * np.sin(x[1])])
-    return _finish(p, f64)
+    return _finish(p, f64, x0)
 
 
 def garch(theta=0.1, omega=0.05, xi=0.1, mu=0.01, x0=(100.0, 0.05), tmax=2.0, f64=False):
     p = SDEProblem(lambda x: jnp.array([mu, theta * (omega - x[1])]),
                    lambda x: jnp.array([[jnp.sqrt(x[1]) * x[0], 0], [0, xi * x[1]]]),
                    x0=list(x0), tmax=tmax)
-    return _finish(p, f64)
+    return _finish(p, f64, x0)
 
 
 def bead_chain(radii, springs, x0, tmax, f64=False):
@@ -67,7 +69,7 @@ def bead_chain(radii, springs, x0, tmax, f64=False):
 
     p = SDEProblem(drift, noise, x0=jnp.array(np.asarray(x0, dtype=np.float64).ravel()), tmax=tmax)
     p.u_ene = u_ene
-    return _finish(p, f64)
+    return _finish(p, f64, x0)
 
 
 def two_spheres(tmax=500.0, f64=False):

@@ -68,6 +68,9 @@ def exp_2d():
     return p, oprob.exp_2d()
 
 
-def as_f64(problem):
-    problem.x0 = np.asarray(problem.x0, dtype=np.float64)
+def as_f64(problem, oracle_problem=None):
+    """Run in double precision: overwrite x0 after construction (the reference's established practice,
+    tests/test_sde_solver.py:119) with the exact double values the oracle twin holds."""
+    src = problem.x0 if oracle_problem is None else np.asarray(oracle_problem.x0).reshape(np.shape(problem.x0))
+    problem.x0 = np.asarray(src, dtype=np.float64)
     return problem

@@ -97,7 +97,9 @@ def test_unknown_scheme_raises():
 
 def _solve_both(prob, oprob, scheme, dt, n, dtype, **kw):
     if dtype == np.float64:
-        P.as_f64(prob)
+        P.as_f64(prob, oprob)
+    else:
+        oprob.x0 = np.asarray(prob.x0, dtype=np.float64)     # the float32-rounded x0 the product integrates
     solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
     got = solver.solve_many(prob, n_trajectories=n, progress_bar=False, **kw)
     okw = {k: v for k, v in kw.items() if k in ("seed", "chunk_size", "chunks_per_randomization")}
