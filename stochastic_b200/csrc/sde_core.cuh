@@ -150,23 +150,6 @@ static __constant__ double ERFINV64_GE16[17] = {
     7.5995277030017761139e-05,  -0.00021503011930044477347, -0.00013871931833623122026, 1.0103004648645343977,
     4.8499064014085844221};
 
-__device__ __forceinline__ float erfinv_xla(float x) {
-    float w = -log1pf(-x * x);
-    float p;
-    if (w < 5.0f) {
-        w = w - 2.5f;
-        p = ERFINV32_LT5[0];
-#pragma unroll
-        for (int i = 1; i < 9; ++i) p = fmaf(p, w, ERFINV32_LT5[i]);
-    } else {
-        w = sqrtf(w) - 3.0f;
-        p = ERFINV32_GE5[0];
-#pragma unroll
-        for (int i = 1; i < 9; ++i) p = fmaf(p, w, ERFINV32_GE5[i]);
-    }
-    return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7f800000) : p * x;
-}
-
 // Lg1..Lg7 of fdlibm's e_log.c, then ln2_hi, ln2_lo
 static __constant__ double LOGC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                       2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
@@ -211,15 +194,25 @@ __device__ __forceinline__ double neg_log_one_minus_sq(double x) {
     return fma(-dk, LOGC[7], inner);
 }
 
-__device__ __forceinline__ double erfinv_xla(double x) {
-    double w = neg_log_one_minus_sq(x);
+// erf_inv is split into the branch-free central polynomial (evaluated for a whole group of draws with
+// the Horner chains interleaved) and a rarely taken tail fix-up (probability ~1e-3 per draw in double).
+__device__ __forceinline__ float erfinv_w(float x) { return -log1pf(-x * x); }
+__device__ __forceinline__ double erfinv_w(double x) { return neg_log_one_minus_sq(x); }
+
+__device__ __forceinline__ bool erfinv_is_central(float w) { return w < 5.0f; }
+__device__ __forceinline__ bool erfinv_is_central(double w) { return w < 6.25; }
+
+static __device__ __noinline__ float erfinv_tail(float x, float w) {
+    w = sqrtf(w) - 3.0f;
+    float p = ERFINV32_GE5[0];
+#pragma unroll 1
+    for (int i = 1; i < 9; ++i) p = fmaf(p, w, ERFINV32_GE5[i]);
+    return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7f800000) : p * x;
+}
+
+static __device__ __noinline__ double erfinv_tail(double x, double w) {
     double p;
-    if (w < 6.25) {
-        w = w - 3.125;
-        p = ERFINV64_LT6_25[0];
-#pragma unroll
-        for (int i = 1; i < 23; ++i) p = fma(p, w, ERFINV64_LT6_25[i]);
-    } else if (w < 16.0) {
+    if (w < 16.0) {
         w = sqrt(w) - 3.25;
         p = ERFINV64_LT16[0];
 #pragma unroll 1
@@ -249,13 +242,61 @@ __device__ __forceinline__ float uniform_pm1(u32 bits) {
     return fmaxf(lo, u);
 }
 
+// N standard normals at once: out[i] = element e[i] of jax.random.normal(key[i], shape with size[i]
+// elements, dtype).  Every stage is written group-wide so that the N dependent chains (20 threefry
+// rounds, the log, the 22-step Horner recurrence) are interleaved in the instruction stream.
+template <int N>
+__device__ __forceinline__ void normal_group(const Key (&key)[N], const u32 (&e)[N], const u32 (&size)[N],
+                                             real (&out)[N]) {
+    real x[N], w[N], p[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#if SDE_F64
+        x[i] = uniform_pm1(random_bits64(key[i], e[i], size[i]));
+#else
+        x[i] = uniform_pm1(random_bits32(key[i], e[i], size[i]));
+#endif
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = erfinv_w(x[i]);
+#if SDE_F64
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = ERFINV64_LT6_25[0];
+#pragma unroll
+    for (int c = 1; c < 23; ++c) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], w[i] - 3.125, ERFINV64_LT6_25[c]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        real v = p[i] * x[i];
+        if (!erfinv_is_central(w[i])) v = erfinv_tail(x[i], w[i]);
+        out[i] = 1.4142135623730951 * v;
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = ERFINV32_LT5[0];
+#pragma unroll
+    for (int c = 1; c < 9; ++c) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fmaf(p[i], w[i] - 2.5f, ERFINV32_LT5[c]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        real v = p[i] * x[i];
+        if (!erfinv_is_central(w[i])) v = erfinv_tail(x[i], w[i]);
+        out[i] = 1.41421354f * v;
+    }
+#endif
+}
+
 // one standard normal: element e of jax.random.normal(key, shape with `size` elements, dtype)
 __device__ __forceinline__ real normal_elem(Key key, u32 e, u32 size) {
-#if SDE_F64
-    return 1.4142135623730951 * erfinv_xla(uniform_pm1(random_bits64(key, e, size)));
-#else
-    return 1.41421354f * erfinv_xla(uniform_pm1(random_bits32(key, e, size)));
-#endif
+    const Key k[1] = {key};
+    const u32 ee[1] = {e}, ss[1] = {size};
+    real o[1];
+    normal_group<1>(k, ee, ss, o);
+    return o[0];
 }
 
 // ----------------------------------------------------------------------------------------
@@ -366,8 +407,13 @@ struct WienerGen {
 #if SDE_M == 1
         // closed forms, reference vectorized_I_generation.py:265-294
 #if SDE_SCHEME == SDE_WAGNER_PLATEN
-        const real u0 = normal_elem(k0, s, 2u * S);
-        const real u1 = normal_elem(k0, S + s, 2u * S);
+        real u01[2];
+        {
+            const Key kk[2] = {k0, k0};
+            const u32 ee[2] = {s, S + s}, ss[2] = {2u * S, 2u * S};
+            normal_group<2>(kk, ee, ss, u01);
+        }
+        const real u0 = u01[0], u1 = u01[1];
         const real dZ = RC(0.5) * (u0 + RC(0.57735026918962576451) * u1);
         I.dW[0] = sc.sqrt_dt * u0;
         I.Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
@@ -388,8 +434,16 @@ struct WienerGen {
 #pragma unroll
         for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * SDE_STAGE(j);
 #else
+        {
+            Key kk[SDE_M];
+            u32 ee[SDE_M], ss[SDE_M];
+            real nn[SDE_M];
 #pragma unroll
-        for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * normal_elem(k0, s * SDE_M + j, S * SDE_M);
+            for (int j = 0; j < SDE_M; ++j) { kk[j] = k0; ee[j] = s * SDE_M + j; ss[j] = S * SDE_M; }
+            normal_group<SDE_M>(kk, ee, ss, nn);
+#pragma unroll
+            for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * nn[j];
+        }
 #endif
 #elif SDE_SCHEME == SDE_MILSTEIN
         gen_milstein(s, sc, I);
@@ -404,10 +458,19 @@ struct WienerGen {
     __device__ __forceinline__ void gen_milstein(u32 s, const StepScale& sc, Integrals& I) const {
         constexpr int M = SDE_M, P = SDE_P;
         real xi[M], mu[M];
+        {
+            Key kk[2 * M];
+            u32 ee[2 * M], ss[2 * M];
+            real nn[2 * M];
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            xi[j] = normal_elem(k_xi, s * M + j, S * M);
-            mu[j] = normal_elem(k_mu, s * M + j, S * M);
+            for (int j = 0; j < M; ++j) {
+                kk[j] = k_xi; kk[M + j] = k_mu;
+                ee[j] = ee[M + j] = s * M + j;
+                ss[j] = ss[M + j] = S * M;
+            }
+            normal_group<2 * M>(kk, ee, ss, nn);
+#pragma unroll
+            for (int j = 0; j < M; ++j) { xi[j] = nn[j]; mu[j] = nn[M + j]; }
         }
         real ser[M][M];  // upper triangle: sum_r (1/r) (zeta_ri a_rj - a_ri zeta_rj)
 #pragma unroll
@@ -417,11 +480,19 @@ struct WienerGen {
 #pragma unroll 1
         for (int r = 1; r <= P; ++r) {
             real a[M], z[M];
+            {
+                Key kk[2 * M];
+                u32 ee[2 * M], ss[2 * M];
+                real nn[2 * M];
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                const u32 e = (s * P + (r - 1)) * M + j;
-                a[j] = fma(RC(1.4142135623730950488), xi[j], normal_elem(k_eta, e, S * P * M));
-                z[j] = normal_elem(k_zeta, e, S * P * M);
+                for (int j = 0; j < M; ++j) {
+                    kk[j] = k_eta; kk[M + j] = k_zeta;
+                    ee[j] = ee[M + j] = (s * P + (r - 1)) * M + j;
+                    ss[j] = ss[M + j] = S * P * M;
+                }
+                normal_group<2 * M>(kk, ee, ss, nn);
+#pragma unroll
+                for (int j = 0; j < M; ++j) { a[j] = fma(RC(1.4142135623730950488), xi[j], nn[j]); z[j] = nn[M + j]; }
             }
             const real rec = RC(1.0) / (real)r;
 #pragma unroll
@@ -464,26 +535,31 @@ struct WienerGen {
             const u32 base = s * (u32)(P * M), size = S * (u32)(P * M);
 #pragma unroll 1
             for (int r = 0; r < P; ++r) {
-                real z[M], h[M];
+                Key kk[2 * M];
+                u32 ee[2 * M], ss[2 * M];
+                real nn[2 * M];
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                    z[j] = normal_elem(k_zeta, base + r * M + j, size);
-                    h[j] = normal_elem(k_eta, base + r * M + j, size);
+                    kk[j] = k_zeta; kk[M + j] = k_eta;
+                    ee[j] = ee[M + j] = base + r * M + j;
+                    ss[j] = ss[M + j] = size;
                 }
+                normal_group<2 * M>(kk, ee, ss, nn);
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                    SDE_STAGE(r * M + j) = z[j];
-                    SDE_STAGE(P * M + r * M + j) = h[j];
+                    SDE_STAGE(r * M + j) = nn[j];
+                    SDE_STAGE(P * M + r * M + j) = nn[M + j];
                 }
             }
 #pragma unroll 1
             for (int j = 0; j < M; ++j) {
-                const real n0 = normal_elem(k_xi, s * M + j, S * M);
-                const real n1 = normal_elem(k_mu, s * M + j, S * M);
-                const real n2 = normal_elem(k_phi, s * M + j, S * M);
-                SDE_STAGE(2 * P * M + j) = n0;
-                SDE_STAGE(2 * P * M + M + j) = n1;
-                SDE_STAGE(2 * P * M + 2 * M + j) = n2;
+                const Key kk[3] = {k_xi, k_mu, k_phi};
+                const u32 ee[3] = {s * M + j, s * M + j, s * M + j}, ss[3] = {S * M, S * M, S * M};
+                real nn[3];
+                normal_group<3>(kk, ee, ss, nn);
+                SDE_STAGE(2 * P * M + j) = nn[0];
+                SDE_STAGE(2 * P * M + M + j) = nn[1];
+                SDE_STAGE(2 * P * M + 2 * M + j) = nn[2];
             }
         }
         real xi[M], a[M], b[M];

@@ -1,0 +1,253 @@
+"""CPU tests of the host side: tracer, symbolic Taylor-Ito tensors, emitter, problem validation,
+chunk arithmetic and the analytic moments module.  No GPU, no compute calls into the CUDA library."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import stochastic_b200 as pychastic
+import stochastic_b200.numpy as jnp
+from stochastic_b200 import grpy, workloads
+from stochastic_b200.sde_solver import L_t_operator, L_w_operator, build_source, chunk_arithmetic
+from stochastic_b200.trace import emit
+from stochastic_b200.trace import expr as E
+from stochastic_b200.trace.taylor import TracedProblem, step_expressions
+from oracle import problems as oprob, rpy as orpy, solver as osolver, taylor_ito
+
+import problems as P
+
+
+# -- SDEProblem ---------------------------------------------------------------------------------
+def test_problem_scalar_and_vector_inputs():
+    """reference tests/test_sde_problem.py"""
+    p = pychastic.sde_problem.SDEProblem(lambda x: jnp.array(0), lambda x: jnp.array(0), 0, 1)
+    assert (p.dimension, p.noise_terms, p.x0.shape) == (1, 1, (1,))
+    p = pychastic.sde_problem.SDEProblem(lambda x: jnp.zeros(2), lambda x: jnp.zeros((2, 3)), jnp.zeros(2), 1)
+    assert (p.dimension, p.noise_terms) == (2, 3)
+    assert p.x0.dtype == np.float32          # reference sde_problem.py:51
+
+
+def test_problem_validation_errors():
+    with pytest.raises(ValueError):
+        pychastic.sde_problem.SDEProblem(lambda x: x, lambda x: x, 1.0, tmax=0)
+    with pytest.raises(ValueError):
+        pychastic.sde_problem.SDEProblem(lambda x: jnp.zeros(3), lambda x: jnp.zeros((2, 2)), jnp.zeros(2), 1)
+    with pytest.raises(ValueError):
+        pychastic.sde_problem.SDEProblem(lambda x: jnp.zeros(2), lambda x: jnp.zeros(2), jnp.zeros(2), 1)
+    p = pychastic.sde_problem.SDEProblem(lambda x: jnp.zeros(2), lambda x: jnp.zeros((2, 2)), jnp.zeros((5, 2)), 1)
+    assert p.x0.shape == (5, 2) and p.dimension == 2
+
+
+def test_x64_switch():
+    pychastic.config.update("enable_x64", True)
+    try:
+        p = pychastic.sde_problem.SDEProblem(lambda x: x, lambda x: x, 0.1, 1.0)
+        assert p.x0.dtype == np.float64 and p.x0[0] == 0.1
+    finally:
+        pychastic.config.update("enable_x64", False)
+
+
+# -- host arithmetic ------------------------------------------------------------------------------
+@pytest.mark.parametrize("tmax,dt,chunk,cpr", [(2.0, 2 ** -8, 1, None), (1.0, 1 / 23, 3, 2), (1.0, 0.01, None, None),
+                                               (8000.0, 0.05, 40, 1), (1.0, 0.3, 1, None), (2.0, 2 ** -10, 1, 3)])
+def test_chunk_arithmetic_matches_oracle(tmax, dt, chunk, cpr):
+    assert chunk_arithmetic(tmax, dt, chunk, cpr) == osolver.chunk_arithmetic(tmax, dt, chunk, cpr)
+
+
+def test_chunk_arithmetic_overshoot():
+    chunk, n_chunks, cpr, n_frag = chunk_arithmetic(1.0, 1 / 23, 3, 2)
+    assert (chunk, n_chunks, cpr, n_frag) == (3, 8, 2, 4)      # 24 steps integrated for 23 needed
+
+
+def test_unknown_scheme_raises_before_touching_the_gpu():
+    prob = workloads.gbm()
+    with pytest.raises(ValueError):
+        pychastic.sde_solver.SDESolver(scheme="heun").solve_many(prob, 4)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        pychastic.sde_solver.SDESolver().solve_many(workloads.gbm(), 4)
+
+
+# -- L operators (the reference's own known-answer tests) -------------------------------------------
+def _L(f, idx, problem):
+    for c in reversed(idx):
+        f = L_t_operator(f, problem) if c == "t" else L_w_operator(f, problem)
+    return f
+
+
+def test_L_operator_logic_1d():
+    """reference tests/test_coefficient_function_logic_1d.py:43-56"""
+    problem = pychastic.sde_problem.SDEProblem(a=lambda x: jnp.exp(3.0 * x), b=lambda x: jnp.exp(7.0 * x), tmax=1.0,
+                                               x0=jnp.array(0.0))
+    x0 = np.array([0.0])
+    ident = lambda x: x
+    got = [np.squeeze(_L(ident, k, problem)(x0)) for k in ("t", "w", "ww", "tw", "wt")]
+    assert np.allclose(got, [1.0, 1.0, 7.0, 7.0 + 0.5 * 7.0 * 7.0, 3.0])
+
+
+def test_L_operator_logic_2d():
+    """reference tests/test_coefficient_function_logic_2d.py:48-67 (index order of f_ww, f_wt)"""
+    problem, _ = P.exp_2d()
+    x0 = np.zeros(2)
+    ident = lambda x: x
+    f_t, f_w, f_ww, f_wt = (np.squeeze(_L(ident, k, problem)(x0)) for k in ("t", "w", "ww", "wt"))
+    a = np.array([1.1, 1.2])
+    b = np.array([[1.3, 1.4], [1.5, 1.6]])
+    bp = np.array([[[1.3 * 7, 0], [0, 1.6 * 17]], [[0, 1.4 * 11], [1.5 * 13, 0]]])
+    ap = np.array([[1.1 * 3, 0], [0, 1.2 * 5]])
+    assert np.allclose(f_t, a) and np.allclose(f_w, b)
+    assert np.allclose(f_ww, np.einsum("ai,abj->bij", b, bp))
+    assert np.allclose(f_wt, np.einsum("cj,cd->dj", b, ap))
+
+
+# -- symbolic coefficient tensors vs autodiff oracle ---------------------------------------------------
+CASES = {
+    "polar_drift": (lambda: P.polar_walk(4.0, (2.0, 0.0)), [1.7, 0.4]),
+    "exp_2d": (P.exp_2d, [0.01, -0.02]),
+    "garch": (P.garch, [90.0, 0.07]),
+    "parabolic": (P.parabolic_walk, [1.1, 0.2]),
+    "gbm": (P.gbm, [1.3]),
+    "arctan": (P.arctan, [0.3]),
+    "tanh": (P.tanh_benchmark, [0.4]),
+    "sinh": (P.sinh_drift, [0.2]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_symbolic_coefficients_match_autodiff(name):
+    mk, x0 = CASES[name]
+    prob, op = mk()
+    tp = TracedProblem(prob.a, prob.b, len(x0))
+    cf = tp.coefficients("wagner_platen")
+    ref = taylor_ito.coefficient_functions(op.a, op.b)
+    xt = torch.tensor(x0, dtype=torch.float64)
+    for k, v in cf.items():
+        flat = [E.wrap(e) for e in np.array(v, dtype=object).ravel()]
+        got = np.array([float(z) for z in E.evaluate(flat, np.array(x0))])
+        want = ref[k](xt).numpy().ravel()
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12), k
+
+
+def test_structural_zeros_are_dropped():
+    """GARCH: b is diagonal, a_0 constant -> most Wagner-Platen tensors are structurally zero."""
+    prob, _ = P.garch()
+    tp = TracedProblem(prob.a, prob.b, 2)
+    cf = tp.coefficients("wagner_platen")
+    f_www = np.array(cf["f_www"], dtype=object)
+    zeros = sum(1 for e in f_www.ravel() if e.is_const and e.value == 0.0)
+    assert zeros >= 11 and f_www.size == 16
+
+
+def _compile_c_step(prob, d, scheme):
+    tp = TracedProblem(prob.a, prob.b, d)
+    outs, sv = step_expressions(tp, scheme)
+    names = {}
+    for i in range(d):
+        names[i] = f"x[{i}]"
+    names[sv.dt] = "dt"
+    for idx in range(d + 1, sv.count):
+        names[idx] = f"I[{idx - d - 1}]"
+    body = emit.emit_body([(f"xn[{i}]", e) for i, e in enumerate(outs)], names, f64=True, lang="c")
+    src = ("#define _GNU_SOURCE\n#include <math.h>\n#include <stdbool.h>\ntypedef double real;\n"
+           "void step(const real* x, const real* I, real dt, real* xn) {\n" + body + "\n}\n")
+    tmp = tempfile.mkdtemp()
+    c, so = os.path.join(tmp, "step.c"), os.path.join(tmp, "step.so")
+    open(c, "w").write(src)
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", so, c, "-lm"])
+    lib = ctypes.CDLL(so)
+    lib.step.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_double, ctypes.c_void_p]
+    return lib, sv
+
+
+@pytest.mark.parametrize("name", ["polar_drift", "garch", "parabolic"])
+def test_emitted_step_compiled_as_c_matches_oracle_step(name):
+    """The emitter's text (the same body NVRTC compiles) run on the host against the oracle's contraction."""
+    mk, x0 = CASES[name]
+    prob, op = mk()
+    d, m = 2, 2
+    lib, sv = _compile_c_step(prob, d, "wagner_platen")
+    rng = np.random.default_rng(5)
+    dt = 0.01
+    I = rng.normal(size=sv.count - d - 1) * 0.1
+    x = np.array(x0, dtype=np.float64)
+    xn = np.zeros(d)
+    lib.step(x.ctypes.data, I.ctypes.data, dt, xn.ctypes.data)
+    cf = {k: f(torch.tensor(x)).numpy() for k, f in taylor_ito.coefficient_functions(op.a, op.b).items()}
+    off = 0
+    dW = I[off:off + m]; off += m
+    Iww = I[off:off + m * m].reshape(m, m); off += m * m
+    Iwt = I[off:off + m]; off += m
+    Itw = I[off:off + m]; off += m
+    Iwww = I[off:off + m ** 3].reshape(m, m, m)
+    want = (x + cf["f_t"].reshape(d) * dt + cf["f_w"] @ dW + np.einsum("ijk,jk->i", cf["f_ww"], Iww)
+            + cf["f_tw"].reshape(d, m) @ Itw + cf["f_wt"].reshape(d, m) @ Iwt
+            + np.einsum("ijkl,jkl->i", cf["f_www"], Iwww) + cf["f_tt"].reshape(d) * dt * dt / 2)
+    assert np.allclose(xn, want, rtol=1e-12, atol=1e-13)
+
+
+def test_generated_source_is_deterministic_and_cached_by_content():
+    prob = workloads.polar_walk(4.0, (2.0, 0.0))
+    s1 = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original")[0]
+    s2 = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original")[0]
+    assert s1 == s2 and "sincos" in s1 and "#define SDE_SCHEME 2" in s1
+
+
+# -- tracer details ----------------------------------------------------------------------------------
+def test_grad_composes_inside_traced_functions():
+    u = lambda x: jnp.sum(x ** 2) * jnp.sin(x[0])
+    g = pychastic.grad(u)(np.array([0.3, -0.7]))
+    want = np.array([2 * 0.3 * np.sin(0.3) + (0.09 + 0.49) * np.cos(0.3), 2 * -0.7 * np.sin(0.3)])
+    assert np.allclose(g, want)
+    h = pychastic.hessian(u)(np.array([0.3, -0.7]))
+    assert np.allclose(h, h.T) and h.shape == (2, 2)
+
+
+def test_where_and_comparisons_trace():
+    x = jnp.symbols((2,))
+    y = jnp.where(x[0] > x[1], x[0], jnp.maximum(x[1], 0.0))
+    vals = E.evaluate([E.wrap(y)], np.array([[2.0, 1.0], [1.0, 3.0], [-5.0, -1.0]]))[0]
+    assert vals.tolist() == [2.0, 3.0, 0.0]
+    with pytest.raises(TypeError):
+        bool(x[0] > 0)
+
+
+def test_rpy_mobility_matches_oracle_in_all_branches():
+    radii = np.array([3.0, 1.0, 1.0, 1.0])
+    for centres in ([[-2.0, 0, 0], [2.0, 0, 0], [6.0, 0, 0], [10.0, 0, 0]],         # touching + far
+                    [[0.0, 0, 0], [2.5, 0.5, 0], [3.0, 1.0, 0.2], [0.5, 0.2, 0.1]]):  # overlapping + immersed
+        c = np.array(centres)
+        want = orpy.muTT_numpy(c, radii)
+        assert np.allclose(grpy.muTT(c, radii), want, rtol=1e-13)
+        x = jnp.symbols((12,))
+        traced = grpy.muTT(jnp.reshape(x, (4, 3)), radii)
+        vals = E.evaluate([E.wrap(v) for v in np.asarray(traced, dtype=object).ravel()], c.ravel())
+        assert np.allclose(np.array([float(v) for v in vals]).reshape(12, 12), want, rtol=1e-12)
+
+
+def test_symbolic_cholesky():
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(4, 4))
+    A = A @ A.T + 4 * np.eye(4)
+    x = jnp.symbols((16,))
+    L = jnp.linalg.cholesky(jnp.reshape(x, (4, 4)))
+    vals = E.evaluate([E.wrap(v) for v in np.asarray(L, dtype=object).ravel()], A.ravel())
+    assert np.allclose(np.array([float(v) for v in vals]).reshape(4, 4), np.linalg.cholesky(A))
+
+
+# -- analytic moments ----------------------------------------------------------------------------------
+def test_wiener_integral_moments_known_values():
+    wim = pychastic.wiener_integral_moments
+    assert wim.E([1, 1])(1) == 0 and wim.E([0, 0])(1) == 0.5
+    assert wim.E2([1, 1])(1) == 0.5
+    assert np.isclose(wim.E2([1, 0])(1), 1 / 3) and np.isclose(wim.E2([0, 1])(1), 1 / 3)
+    assert np.isclose(wim.E2([1, 0], [0, 1])(1), 1 / 6)
+    assert np.isclose(wim.E2([1, 2, 1])(1), 1 / 6) and wim.E2([1, 2, 1], [2, 1, 1])(1) == 0
+    assert np.isclose(wim.E2([1], [1, 0])(2.0), 2.0)      # t^2 / 2
