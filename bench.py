@@ -136,10 +136,10 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    n_sample, dt_exp = 125 * procs, 6
+    n_sample, dt_exp = 2000 * procs, 5
     rates = []
     for _ in range(args.warmup):
-        cpu_port_rate(max(procs, n_sample // 8), dt_exp, procs)
+        cpu_port_rate(max(procs, n_sample // 16), dt_exp, procs)
     t_all = time.perf_counter()
     for _ in range(args.steps):
         r, el, n_used = cpu_port_rate(n_sample, dt_exp, procs)
@@ -274,9 +274,9 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             procs = max(1, min(cores, 64))
-            r, el, n_used = cpu_port_rate(125 * procs, 6, procs)
+            r, el, n_used = cpu_port_rate(2000 * procs, 5, procs)
             cpu = {"value": r, "unit": UNIT, "cores": procs, "kind": "port",
-                   "sample": f"{n_used} trajectories x 64 steps (dt=2^-6) of the same workload, {el:.1f} s, "
+                   "sample": f"{n_used} trajectories x 32 steps (dt=2^-5) of the same workload, {el:.1f} s, "
                              f"{procs} processes; numpy/torch.func port of the reference (JAX unavailable)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

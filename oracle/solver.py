@@ -22,7 +22,7 @@ import torch
 
 from . import jax_prng
 from .taylor_ito import batched_coefficient_functions
-from .wiener_integrals import get_wiener_integrals
+from .wiener_integrals import get_wiener_integrals_many
 
 SCHEMES = ("euler", "milstein", "wagner_platen")
 
@@ -114,10 +114,7 @@ def solve_many(problem, scheme="euler", dt=0.01, n_trajectories=1, seed=0, chunk
     frag_keys = np.stack([jax_prng.split(k, n_frag, layout) for k in keys])      # (n, n_frag, 2)
     n_run = n_frag if max_fragments is None else min(n_frag, max_fragments)
     for fr in range(n_run):
-        per_traj = [get_wiener_integrals(frag_keys[i, fr], steps=S, noise_terms=m, scheme=scheme,
-                                         p=p, dtype=dt_np, layout=layout) for i in range(n)]
-        I = {k: np.stack([pt[k].reshape((S,) + pt[k].shape[1:] if pt[k].ndim > 1 else (S, m))
-                          for pt in per_traj]) for k in per_traj[0]}
+        I = get_wiener_integrals_many(frag_keys[:, fr], S, m, scheme, p=p, dtype=dt_np, layout=layout)
         for c in range(cpr):
             for k in range(chunk):
                 s = c * chunk + k

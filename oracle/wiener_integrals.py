@@ -112,30 +112,30 @@ def batched_D_mat(eta, zeta):
     # first sum, l, r in 1..p, index l + r
     c = (1.0 / (r1 * (l1 + r1))).astype(dt)
     zs, es = Z[..., l1 + r1], E[..., l1 + r1]                # [s, j, l, r]
-    s1 = (np.einsum("lr,sbl,sclr,sar->sabc", c, zl, zs, er)
-          - np.einsum("lr,sbl,scr,salr->sabc", c, zl, zr, es)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr, zs)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er, es))
+    s1 = (np.einsum("lr,sbl,sclr,sar->sabc", c, zl, zs, er, optimize=True)
+          - np.einsum("lr,sbl,scr,salr->sabc", c, zl, zr, es, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr, zs, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er, es, optimize=True))
 
     # second sum, r < l, index l - r
     with np.errstate(divide="ignore", invalid="ignore"):
         c = np.where(r2 < l1, 1.0 / (r2 * np.where(r2 < l1, l1 - r2, 1)), 0.0).astype(dt)
     idx = np.clip(l1 - r2, 0, 2 * p)
     zd, ed = Z[..., idx], E[..., idx]
-    s2 = (np.einsum("lr,sbl,sar,sclr->sabc", c, zl, zr2, ed)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, zl, er2, zd)
-          - np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr2, zd)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er2, ed))
+    s2 = (np.einsum("lr,sbl,sar,sclr->sabc", c, zl, zr2, ed, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, zl, er2, zd, optimize=True)
+          - np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr2, zd, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er2, ed, optimize=True))
 
     # third sum, r > l (r up to 2p, reads beyond p are zero), index r - l
     with np.errstate(divide="ignore", invalid="ignore"):
         c = np.where(r2 > l1, 1.0 / (r2 * np.where(r2 > l1, r2 - l1, 1)), 0.0).astype(dt)
     idx = np.clip(r2 - l1, 0, 2 * p)
     zd, ed = Z[..., idx], E[..., idx]
-    s3 = (np.einsum("lr,sbl,sclr,sar->sabc", c, zl, zd, er2)
-          - np.einsum("lr,sbl,sar,sclr->sabc", c, zl, zr2, ed)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr2, zd)
-          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er2, ed))
+    s3 = (np.einsum("lr,sbl,sclr,sar->sabc", c, zl, zd, er2, optimize=True)
+          - np.einsum("lr,sbl,sar,sclr->sabc", c, zl, zr2, ed, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, zr2, zd, optimize=True)
+          + np.einsum("lr,sbl,sar,sclr->sabc", c, el, er2, ed, optimize=True))
 
     return (dt.type(1.0 / (np.pi ** 2 * 2 ** 2.5)) * (-s1 + s2 + s3)).astype(dt)
 
@@ -155,27 +155,48 @@ def _fill_diag(mat, vec):
     return out
 
 
-def get_wiener_integrals(key, steps=1, noise_terms=1, scheme="euler", p=10,
-                         dtype=np.float32, layout="original"):
-    """Unit-step integrals for `steps` steps; same dict keys and shapes as the reference."""
+def draw_normals(key, steps, noise_terms, scheme, p=10, dtype=np.float32, layout="original"):
+    """The raw normal draws of one key, in the reference's key order (dict of arrays with leading axis S)."""
     dt = np.dtype(dtype)
-    f = dt.type
-    m = noise_terms
-    S = steps
+    m, S = noise_terms, steps
 
     def nrm(k, shape):
         return jax_prng.normal(k, shape, dt, layout)
 
     if m == 1:
-        if scheme == "euler":
-            return {"d_w": nrm(key, (S, 1))}
-        if scheme == "milstein":
-            dW = nrm(key, (S, 1))
-            return {"d_w": dW, "d_ww": (f(0.5) * (dW ** 2 - f(1)))[..., None]}
+        if scheme in ("euler", "milstein"):
+            return {"u": nrm(key, (S, 1))}
         if scheme == "wagner_platen":
             u = nrm(key, (2, S, 1))
-            dW = u[0]
-            dZ = (f(0.5) * (u[0] + f(3 ** -0.5) * u[1]))[..., None]
+            return {"u0": u[0], "u1": u[1]}
+    if scheme == "euler":
+        return {"u": nrm(key, (S, m))}
+    if scheme == "milstein":
+        k1, k2, k3, k4 = jax_prng.split(key, 4, layout)
+        return {"xi": nrm(k1, (S, 1, m))[:, 0], "mu": nrm(k2, (S, 1, m))[:, 0], "eta": nrm(k3, (S, p, m)),
+                "zeta": nrm(k4, (S, p, m))}
+    if scheme == "wagner_platen":
+        k1, k2, k3, k4, k5 = jax_prng.split(key, 5, layout)
+        return {"xi": nrm(k1, (S, m)), "zeta": nrm(k2, (S, p, m)), "eta": nrm(k3, (S, p, m)), "mu": nrm(k4, (S, m)),
+                "phi": nrm(k5, (S, m))}
+    raise NotImplementedError(scheme)
+
+
+def assemble_integrals(draws, noise_terms, scheme, p=10, dtype=np.float32):
+    """Draws (leading axis = any batch of steps) -> unit-step integrals, reference shapes with leading axis S."""
+    dt = np.dtype(dtype)
+    f = dt.type
+    m = noise_terms
+    if m == 1:
+        if scheme == "euler":
+            return {"d_w": draws["u"]}
+        if scheme == "milstein":
+            dW = draws["u"]
+            return {"d_w": dW, "d_ww": (f(0.5) * (dW ** 2 - f(1)))[..., None]}
+        if scheme == "wagner_platen":
+            u0, u1 = draws["u0"], draws["u1"]
+            dW = u0
+            dZ = (f(0.5) * (u0 + f(3 ** -0.5) * u1))[..., None]
             return {
                 "d_w": dW,
                 "d_ww": (f(0.5) * (dW ** 2 - f(1)))[..., None],
@@ -183,36 +204,23 @@ def get_wiener_integrals(key, steps=1, noise_terms=1, scheme="euler", p=10,
                 "d_tw": dW[..., None] - dZ,
                 "d_www": (f(0.5) * (f(1.0 / 3.0) * dW ** 2 - f(1)) * dW)[..., None, None],
             }
-
     if scheme == "euler":
-        return {"d_w": nrm(key, (S, m))}
+        return {"d_w": draws["u"]}
 
     rec = (1.0 / np.arange(1, p + 1)).astype(dt)
     if scheme == "milstein":
-        k1, k2, k3, k4 = jax_prng.split(key, 4, layout)
-        xi = nrm(k1, (S, 1, m))
-        mu = nrm(k2, (S, 1, m))
-        eta = nrm(k3, (S, p, m))
-        zeta = nrm(k4, (S, p, m))
+        x, u, eta, zeta = draws["xi"], draws["mu"], draws["eta"], draws["zeta"]
         rho = f(1 / 12 - (rec.astype(np.float64) ** 2).sum() / (2 * np.pi ** 2))
-        a = f(np.sqrt(2)) * xi + eta                                   # (S, p, m)
-        x = xi[:, 0, :]
-        u = mu[:, 0, :]
+        a = f(np.sqrt(2)) * x[:, None, :] + eta                                   # (S, p, m)
         series = np.einsum("r,sri,srj->sij", rec, zeta, a) - np.einsum("r,sri,srj->sij", rec, a, zeta)
         I = (x[:, :, None] * x[:, None, :] / f(2)
              + np.sqrt(rho) * (x[:, :, None] * u[:, None, :] - u[:, :, None] * x[:, None, :])
              + f(1.0 / (2 * np.pi)) * series).astype(dt)
         I = _fill_diag(I, f(0.5) * (x ** 2 - f(1)))
-        dW = xi.squeeze()
-        return {"d_w": dW, "d_ww": I}
+        return {"d_w": x, "d_ww": I}
 
     if scheme == "wagner_platen":
-        k1, k2, k3, k4, k5 = jax_prng.split(key, 5, layout)
-        xi = nrm(k1, (S, m))
-        zeta = nrm(k2, (S, p, m))
-        eta = nrm(k3, (S, p, m))
-        mu = nrm(k4, (S, m))
-        phi = nrm(k5, (S, m))
+        xi, zeta, eta, mu, phi = draws["xi"], draws["zeta"], draws["eta"], draws["mu"], draws["phi"]
         rec64 = rec.astype(np.float64)
         rho = f(1 / 12 - (rec64 ** 2).sum() / (2 * np.pi ** 2))
         alpha = f(np.pi ** 2 / 180 - (0.5 / np.pi ** 2) * (rec64 ** 4).sum())
@@ -250,10 +258,30 @@ def get_wiener_integrals(key, steps=1, noise_terms=1, scheme="euler", p=10,
         d_www = J - f(0.5) * (eye[None, :, :, None] * d_tw[:, None, None, :]
                               + eye[None, None, :, :] * d_wt[:, :, None, None])
         return {
-            "d_w": xi.squeeze(),
+            "d_w": xi,
             "d_ww": d_ww.astype(dt),
             "d_wt": d_wt[:, :, None].astype(dt),
             "d_tw": d_tw[:, None, :].astype(dt),
             "d_www": d_www.astype(dt),
         }
     raise NotImplementedError(scheme)
+
+
+def get_wiener_integrals(key, steps=1, noise_terms=1, scheme="euler", p=10,
+                         dtype=np.float32, layout="original"):
+    """Unit-step integrals for `steps` steps; same dict keys and shapes as the reference."""
+    draws = draw_normals(key, steps, noise_terms, scheme, p, dtype, layout)
+    out = assemble_integrals(draws, noise_terms, scheme, p, dtype)
+    if noise_terms > 1 and scheme in ("milstein", "wagner_platen"):
+        out["d_w"] = out["d_w"].squeeze()        # the reference's xi.squeeze() (drops the step axis when steps == 1)
+    return out
+
+
+def get_wiener_integrals_many(keys, steps, noise_terms, scheme, p=10, dtype=np.float32, layout="original"):
+    """One call per key for the draws (the reference vmaps over keys), ONE batched assembly for all keys.
+    Returns arrays with leading axes (n_keys, steps)."""
+    per = [draw_normals(k, steps, noise_terms, scheme, p, dtype, layout) for k in keys]
+    cat = {name: np.concatenate([d[name] for d in per], axis=0) for name in per[0]}
+    flat = assemble_integrals(cat, noise_terms, scheme, p, dtype)
+    n = len(keys)
+    return {k: v.reshape((n, steps) + v.shape[1:]) for k, v in flat.items()}
