@@ -334,6 +334,14 @@ struct StepScale {
 #ifndef SDE_BLOCK
 #define SDE_BLOCK 128
 #endif
+// Steps whose integrals are generated together (see WienerGen::generate_block).
+#if SDE_M == 1
+#define SDE_STEP_BLOCK ((SDE_SCHEME == SDE_WAGNER_PLATEN) ? 2 : 4)
+#elif SDE_SCHEME == SDE_EULER && SDE_STAGE_COUNT == 0
+#define SDE_STEP_BLOCK ((SDE_M >= 4) ? 1 : ((SDE_M == 3) ? 1 : 2))
+#else
+#define SDE_STEP_BLOCK 1
+#endif
 // element k of this thread's staging column (stage points at the thread's slot of row 0)
 #define SDE_STAGE(k) stage[(k) * SDE_BLOCK]
 
@@ -403,52 +411,76 @@ struct WienerGen {
 #endif
     }
 
-    __device__ __forceinline__ void generate(u32 s, const StepScale& sc, Integrals& I, real* stage) const {
+    // Integrals of SDE_STEP_BLOCK consecutive steps s0, s0+1, ... (steps past the end of the fragment produce
+    // unused values).  Blocking several steps of a cheap scheme into one group of normals gives the dependent
+    // threefry / Horner chains something to interleave with.
+    __device__ __forceinline__ void generate_block(u32 s0, const StepScale& sc, Integrals (&I)[SDE_STEP_BLOCK],
+                                                   real* stage) const {
 #if SDE_M == 1
         // closed forms, reference vectorized_I_generation.py:265-294
 #if SDE_SCHEME == SDE_WAGNER_PLATEN
-        real u01[2];
-        {
-            const Key kk[2] = {k0, k0};
-            const u32 ee[2] = {s, S + s}, ss[2] = {2u * S, 2u * S};
-            normal_group<2>(kk, ee, ss, u01);
+        constexpr int B = SDE_STEP_BLOCK;
+        Key kk[2 * B];
+        u32 ee[2 * B], ss[2 * B];
+        real nn[2 * B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            kk[b] = k0; kk[B + b] = k0;
+            ee[b] = s0 + b; ee[B + b] = S + s0 + b;
+            ss[b] = ss[B + b] = 2u * S;
         }
-        const real u0 = u01[0], u1 = u01[1];
-        const real dZ = RC(0.5) * (u0 + RC(0.57735026918962576451) * u1);
-        I.dW[0] = sc.sqrt_dt * u0;
-        I.Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
-        I.Iwt[0] = sc.dt32 * dZ;
-        I.Itw[0] = sc.dt32 * (u0 - dZ);
-        I.Iwww[0][0][0] = sc.dt32 * (RC(0.5) * (RC(0.33333333333333333333) * u0 * u0 - RC(1.0)) * u0);
+        normal_group<2 * B>(kk, ee, ss, nn);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const real u0 = nn[b], u1 = nn[B + b];
+            const real dZ = RC(0.5) * (u0 + RC(0.57735026918962576451) * u1);
+            I[b].dW[0] = sc.sqrt_dt * u0;
+            I[b].Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
+            I[b].Iwt[0] = sc.dt32 * dZ;
+            I[b].Itw[0] = sc.dt32 * (u0 - dZ);
+            I[b].Iwww[0][0][0] = sc.dt32 * (RC(0.5) * (RC(0.33333333333333333333) * u0 * u0 - RC(1.0)) * u0);
+        }
 #else
-        const real u0 = normal_elem(k0, s, S);
-        I.dW[0] = sc.sqrt_dt * u0;
+        constexpr int B = SDE_STEP_BLOCK;
+        Key kk[B];
+        u32 ee[B], ss[B];
+        real nn[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) { kk[b] = k0; ee[b] = s0 + b; ss[b] = S; }
+        normal_group<B>(kk, ee, ss, nn);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            I[b].dW[0] = sc.sqrt_dt * nn[b];
 #if SDE_SCHEME == SDE_MILSTEIN
-        I.Iww[0][0] = sc.dt * (RC(0.5) * (u0 * u0 - RC(1.0)));
+            I[b].Iww[0][0] = sc.dt * (RC(0.5) * (nn[b] * nn[b] - RC(1.0)));
 #endif
+        }
 #endif
 #elif SDE_SCHEME == SDE_EULER
 #if SDE_STAGE_COUNT > 0
 #pragma unroll 1
-        for (int j = 0; j < SDE_M; ++j) SDE_STAGE(j) = normal_elem(k0, s * SDE_M + j, S * SDE_M);
+        for (int j = 0; j < SDE_M; ++j) SDE_STAGE(j) = normal_elem(k0, s0 * SDE_M + j, S * SDE_M);
 #pragma unroll
-        for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * SDE_STAGE(j);
+        for (int j = 0; j < SDE_M; ++j) I[0].dW[j] = sc.sqrt_dt * SDE_STAGE(j);
 #else
         {
-            Key kk[SDE_M];
-            u32 ee[SDE_M], ss[SDE_M];
-            real nn[SDE_M];
+            constexpr int N = SDE_M * SDE_STEP_BLOCK;     // elements of consecutive steps are consecutive
+            Key kk[N];
+            u32 ee[N], ss[N];
+            real nn[N];
 #pragma unroll
-            for (int j = 0; j < SDE_M; ++j) { kk[j] = k0; ee[j] = s * SDE_M + j; ss[j] = S * SDE_M; }
-            normal_group<SDE_M>(kk, ee, ss, nn);
+            for (int q = 0; q < N; ++q) { kk[q] = k0; ee[q] = s0 * SDE_M + q; ss[q] = S * SDE_M; }
+            normal_group<N>(kk, ee, ss, nn);
 #pragma unroll
-            for (int j = 0; j < SDE_M; ++j) I.dW[j] = sc.sqrt_dt * nn[j];
+            for (int b = 0; b < SDE_STEP_BLOCK; ++b)
+#pragma unroll
+                for (int j = 0; j < SDE_M; ++j) I[b].dW[j] = sc.sqrt_dt * nn[b * SDE_M + j];
         }
 #endif
 #elif SDE_SCHEME == SDE_MILSTEIN
-        gen_milstein(s, sc, I);
+        gen_milstein(s0, sc, I[0]);
 #else
-        gen_wagner_platen(s, sc, I, stage);
+        gen_wagner_platen(s0, sc, I[0], stage);
 #endif
         (void)stage;
     }

@@ -20,6 +20,11 @@
 #ifndef SDE_MIN_BLOCKS
 #define SDE_MIN_BLOCKS 1
 #endif
+#ifndef SDE_SNAP_TILE
+#define SDE_SNAP_TILE 1     // > 1: stage this many consecutive snapshots per trajectory in shared memory
+#endif
+#define SDE_SNAP_FIELDS (1 + SDE_D + SDE_M)
+#define SDE_SNAP_PITCH 33   // lane pitch of a staged row (bank-conflict padding)
 #ifndef SDE_LOCKSTEP
 #define SDE_LOCKSTEP (SDE_STAGE_COUNT > 0)
 #endif
@@ -55,6 +60,17 @@ extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solve_kernel(const sdeb::SolveArgs A) {
     using namespace sdeb;
     real* const stage = reinterpret_cast<real*>(sde_dyn_smem) + threadIdx.x;
+#if SDE_SNAP_TILE > 1
+    // Snapshot staging: the thread-per-trajectory mapping would store 8 bytes at a stride of a whole trajectory
+    // row.  Instead every warp collects SDE_SNAP_TILE consecutive snapshots of its 32 trajectories in shared
+    // memory and writes them out transposed, so that one store instruction covers contiguous
+    // SDE_SNAP_TILE * sizeof(real) runs of the (trajectory, snapshot, component) output rows.
+    real* const snapbuf = reinterpret_cast<real*>(sde_dyn_smem) + SDE_STAGE_COUNT * SDE_BLOCK +
+                          (threadIdx.x >> 5) * (SDE_SNAP_FIELDS * SDE_SNAP_TILE * SDE_SNAP_PITCH);
+    const int lane = threadIdx.x & 31;
+    const u64 warp_first = (u64)blockIdx.x * SDE_BLOCK + (threadIdx.x & ~31u);
+    u32 tile_fill = 0, tile_snap0 = 0;
+#endif
     const u64 tid_raw = (u64)blockIdx.x * SDE_BLOCK + threadIdx.x;
     const bool active = tid_raw < A.traj_count;
     // Threads past the end integrate trajectory 0 again (no stores): every thread of the CTA then runs the
@@ -87,16 +103,19 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
         for (u32 f = 0; f < A.n_fragments && snap < A.n_snapshots; ++f) {
             WienerGen gen;
             gen.init(split_key(tkey, A.n_fragments, f), S);
-            u32 s = 0;
-            for (u32 c = 0; c < A.cpr && snap < A.n_snapshots; ++c, ++snap) {
-                for (u32 k = 0; k < A.chunk; ++k, ++s) {
+            u32 in_chunk = 0;   // steps taken since the last snapshot
+            for (u32 s0 = 0; s0 < S && snap < A.n_snapshots; s0 += SDE_STEP_BLOCK) {
 #if SDE_LOCKSTEP
-                    // Keep the warps of the CTA on the same stretch of the (large, mostly straight-line) step
-                    // body so that one instruction-cache fill serves all of them.
-                    __syncthreads();
+                // Keep the warps of the CTA on the same stretch of the (large, mostly straight-line) step body so
+                // that one instruction-cache fill serves all of them.
+                __syncthreads();
 #endif
-                    Integrals I;
-                    gen.generate(s, sc, I, stage);
+                Integrals Iblk[SDE_STEP_BLOCK];
+                gen.generate_block(s0, sc, Iblk, stage);
+#pragma unroll
+                for (int b = 0; b < SDE_STEP_BLOCK; ++b) {
+                    if (s0 + b >= S || snap >= A.n_snapshots) break;
+                    const Integrals& I = Iblk[b];
                     t += sc.dt;
                     sde_step(x, I, sc.dt);
 #if SDE_HAS_POST
@@ -104,17 +123,69 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
 #endif
 #pragma unroll
                     for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
-                }
-                const u64 row = tid * (u64)A.n_snapshots + snap;
-                if (!active) continue;
-                if (A.out_t) A.out_t[row] = t;
-                if (A.out_x) {
+                    if (++in_chunk < A.chunk) continue;
+                    in_chunk = 0;
+                    // ---- snapshot `snap` -----------------------------------------------------------------
+#if SDE_SNAP_TILE > 1
+                {
+                    real* col = snapbuf + tile_fill * SDE_SNAP_PITCH + lane;
+                    col[0] = t;
 #pragma unroll
-                    for (int i = 0; i < SDE_D; ++i) A.out_x[row * SDE_D + i] = x[i];
-                }
-                if (A.out_w) {
+                    for (int i = 0; i < SDE_D; ++i) col[(1 + i) * SDE_SNAP_TILE * SDE_SNAP_PITCH] = x[i];
 #pragma unroll
-                    for (int j = 0; j < SDE_M; ++j) A.out_w[row * SDE_M + j] = w[j];
+                    for (int j = 0; j < SDE_M; ++j) col[(1 + SDE_D + j) * SDE_SNAP_TILE * SDE_SNAP_PITCH] = w[j];
+                    if (tile_fill == 0) tile_snap0 = snap;
+                    ++tile_fill;
+                    if (tile_fill == SDE_SNAP_TILE || snap + 1 == A.n_snapshots) {
+                        __syncwarp();
+                        // t: SDE_SNAP_TILE contiguous values per trajectory
+                        if (A.out_t) {
+                            for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE; idx += 32) {
+                                const u32 l = idx / SDE_SNAP_TILE, kk = idx % SDE_SNAP_TILE;
+                                const u64 traj = warp_first + l;
+                                if (traj < A.traj_count && kk < tile_fill)
+                                    A.out_t[traj * A.n_snapshots + tile_snap0 + kk] = snapbuf[kk * SDE_SNAP_PITCH + l];
+                            }
+                        }
+                        if (A.out_x) {
+                            for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE * SDE_D; idx += 32) {
+                                const u32 l = idx / (SDE_SNAP_TILE * SDE_D), rem = idx % (SDE_SNAP_TILE * SDE_D);
+                                const u32 kk = rem / SDE_D, i = rem % SDE_D;
+                                const u64 traj = warp_first + l;
+                                if (traj < A.traj_count && kk < tile_fill)
+                                    A.out_x[(traj * A.n_snapshots + tile_snap0 + kk) * SDE_D + i] =
+                                        snapbuf[((1 + i) * SDE_SNAP_TILE + kk) * SDE_SNAP_PITCH + l];
+                            }
+                        }
+                        if (A.out_w) {
+                            for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE * SDE_M; idx += 32) {
+                                const u32 l = idx / (SDE_SNAP_TILE * SDE_M), rem = idx % (SDE_SNAP_TILE * SDE_M);
+                                const u32 kk = rem / SDE_M, j = rem % SDE_M;
+                                const u64 traj = warp_first + l;
+                                if (traj < A.traj_count && kk < tile_fill)
+                                    A.out_w[(traj * A.n_snapshots + tile_snap0 + kk) * SDE_M + j] =
+                                        snapbuf[((1 + SDE_D + j) * SDE_SNAP_TILE + kk) * SDE_SNAP_PITCH + l];
+                            }
+                        }
+                        __syncwarp();
+                        tile_fill = 0;
+                    }
+                }
+#else
+                    if (active) {
+                        const u64 row = tid * (u64)A.n_snapshots + snap;
+                        if (A.out_t) A.out_t[row] = t;
+                        if (A.out_x) {
+#pragma unroll
+                            for (int i = 0; i < SDE_D; ++i) A.out_x[row * SDE_D + i] = x[i];
+                        }
+                        if (A.out_w) {
+#pragma unroll
+                            for (int j = 0; j < SDE_M; ++j) A.out_w[row * SDE_M + j] = w[j];
+                        }
+                    }
+#endif
+                    ++snap;
                 }
             }
         }
@@ -125,7 +196,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
 #if SDE_NOBS > 0
     // block reduction of sum and sum of squares, one atomicAdd pair per observable per block
     __shared__ double red[2 * SDE_NOBS][SDE_BLOCK / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int red_lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < SDE_NOBS; ++k) {
         double s1 = active ? obs[k] : 0.0;
@@ -135,7 +206,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
             s1 += __shfl_down_sync(0xffffffffu, s1, o);
             s2 += __shfl_down_sync(0xffffffffu, s2, o);
         }
-        if (lane == 0) {
+        if (red_lane == 0) {
             red[2 * k][wid] = s1;
             red[2 * k + 1][wid] = s2;
         }

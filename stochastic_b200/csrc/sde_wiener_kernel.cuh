@@ -34,8 +34,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sde_wiener_kernel(const 
     sc.dt = RC(1.0);
     sc.sqrt_dt = RC(1.0);
     sc.dt32 = RC(1.0);
-    Integrals I;
-    gen.generate(s, sc, I, stage);
+    Integrals Iblk[SDE_STEP_BLOCK];      // the block generator is the production path; only its first step is kept
+    gen.generate_block(s, sc, Iblk, stage);
+    const Integrals& I = Iblk[0];
     constexpr int M = SDE_M;
 #pragma unroll
     for (int j = 0; j < M; ++j) A.d_w[(u64)s * M + j] = I.dW[j];

@@ -113,6 +113,24 @@ def pick_block(m, p, scheme, f64, preferred=None):
     return block
 
 
+def pick_snap_tile(d, m, block, f64, stage_bytes, n_snapshots, budget=96 * 1024):
+    """Snapshots staged per trajectory before a transposed, coalesced write-out (SDE_SNAP_TILE).
+    1 = direct stores (final-only runs); otherwise the largest power of two <= 16 whose staging tiles
+    (one per warp, pitch 33) fit next to the normals staging area in `budget` bytes per CTA."""
+    if n_snapshots < 4:
+        return 1
+    tile = 16
+    while tile > 1:
+        if tile <= n_snapshots and stage_bytes + snap_tile_bytes(d, m, block, f64, tile) <= budget:
+            return tile
+        tile //= 2
+    return 1
+
+
+def snap_tile_bytes(d, m, block, f64, tile):
+    return 0 if tile <= 1 else (block // 32) * (1 + d + m) * tile * 33 * (8 if f64 else 4)
+
+
 def check(status, what=""):
     if status == 0:
         return
