@@ -138,32 +138,38 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
                     ++tile_fill;
                     if (tile_fill == SDE_SNAP_TILE || snap + 1 == A.n_snapshots) {
                         __syncwarp();
-                        // t: SDE_SNAP_TILE contiguous values per trajectory
-                        if (A.out_t) {
+                        // rows of this warp's trajectories start at row0 + l * n_snapshots (l = lane of the owner)
+                        const u64 row0 = warp_first * (u64)A.n_snapshots + tile_snap0;
+                        const u32 lmax = (A.traj_count > warp_first)
+                                             ? (u32)((A.traj_count - warp_first < 32) ? (A.traj_count - warp_first) : 32)
+                                             : 0u;
+                        if (A.out_t) {   // SDE_SNAP_TILE contiguous values per trajectory
+                            real* const dst = A.out_t + row0;
+#pragma unroll 4
                             for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE; idx += 32) {
                                 const u32 l = idx / SDE_SNAP_TILE, kk = idx % SDE_SNAP_TILE;
-                                const u64 traj = warp_first + l;
-                                if (traj < A.traj_count && kk < tile_fill)
-                                    A.out_t[traj * A.n_snapshots + tile_snap0 + kk] = snapbuf[kk * SDE_SNAP_PITCH + l];
+                                if (l < lmax && kk < tile_fill) dst[l * A.n_snapshots + kk] = snapbuf[kk * SDE_SNAP_PITCH + l];
                             }
                         }
-                        if (A.out_x) {
+                        if (A.out_x) {   // SDE_SNAP_TILE * SDE_D contiguous values per trajectory
+                            real* const dst = A.out_x + row0 * SDE_D;
+#pragma unroll 4
                             for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE * SDE_D; idx += 32) {
                                 const u32 l = idx / (SDE_SNAP_TILE * SDE_D), rem = idx % (SDE_SNAP_TILE * SDE_D);
                                 const u32 kk = rem / SDE_D, i = rem % SDE_D;
-                                const u64 traj = warp_first + l;
-                                if (traj < A.traj_count && kk < tile_fill)
-                                    A.out_x[(traj * A.n_snapshots + tile_snap0 + kk) * SDE_D + i] =
+                                if (l < lmax && kk < tile_fill)
+                                    dst[l * A.n_snapshots * SDE_D + rem] =
                                         snapbuf[((1 + i) * SDE_SNAP_TILE + kk) * SDE_SNAP_PITCH + l];
                             }
                         }
                         if (A.out_w) {
+                            real* const dst = A.out_w + row0 * SDE_M;
+#pragma unroll 4
                             for (u32 idx = lane; idx < 32u * SDE_SNAP_TILE * SDE_M; idx += 32) {
                                 const u32 l = idx / (SDE_SNAP_TILE * SDE_M), rem = idx % (SDE_SNAP_TILE * SDE_M);
                                 const u32 kk = rem / SDE_M, j = rem % SDE_M;
-                                const u64 traj = warp_first + l;
-                                if (traj < A.traj_count && kk < tile_fill)
-                                    A.out_w[(traj * A.n_snapshots + tile_snap0 + kk) * SDE_M + j] =
+                                if (l < lmax && kk < tile_fill)
+                                    dst[l * A.n_snapshots * SDE_M + rem] =
                                         snapbuf[((1 + SDE_D + j) * SDE_SNAP_TILE + kk) * SDE_SNAP_PITCH + l];
                             }
                         }

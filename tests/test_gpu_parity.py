@@ -210,3 +210,75 @@ def test_step_post_processing_and_observables():
     assert np.allclose(mom[:, 0], obs.sum(0), rtol=1e-9, atol=1e-9)
     assert np.allclose(mom[:, 1], (obs ** 2).sum(0), rtol=1e-9, atol=1e-9)
     assert got["count"] == 50
+
+
+# ---- the reference's own solver tests, run through the product API ----------------------------------------
+@pytest.mark.parametrize("scheme,name,limit", [("euler", "gbm", 1.4), ("milstein", "gbm", 0.7),
+                                               ("euler", "arctan", 0.09), ("milstein", "arctan", 0.008)])
+def test_reference_scalar_thresholds(scheme, name, limit):
+    """reference tests/test_sde_solver.py:27-47"""
+    prob, _ = P.gbm(1.0, 1.0, 1.0, 1.0) if name == "gbm" else P.arctan()
+    solver = pychastic.sde_solver.SDESolver(scheme=scheme)
+    solver.dt = prob.tmax / 2 ** 7
+    result = solver.solve(prob)
+    t = np.asarray(result["time_values"]).reshape(-1, 1)
+    exact = prob.exact_solution(prob.x0, t, np.asarray(result["wiener_values"]))
+    assert abs((exact - np.asarray(result["solution_values"]))[-1]) < limit
+
+
+@pytest.mark.parametrize("scheme,name,limit", [("euler", "polar", 1.08), ("milstein", "polar", 1.2),
+                                               ("euler", "parabolic", 0.025), ("milstein", "parabolic", 0.002)])
+def test_reference_vector_thresholds(scheme, name, limit):
+    """reference tests/test_sde_solver.py:91-112"""
+    prob, _ = P.polar_walk() if name == "polar" else P.parabolic_walk()
+    solver = pychastic.sde_solver.SDESolver(scheme=scheme)
+    solver.dt = prob.tmax / 2 ** 7
+    result = solver.solve(prob, seed=1)
+    x, w = np.asarray(result["solution_values"]), np.asarray(result["wiener_values"])
+    end_error = prob.to_cartesian(x[-1]) - (w[-1] + prob.to_cartesian(np.asarray(prob.x0)))
+    assert (end_error ** 2).sum() ** 0.5 < limit
+
+
+def test_kp_exercise_9_3_3():
+    """reference tests/test_kloeden_platen_statistics.py: Euler strong error halves with dt (order 1/2 -> here the
+    published 0.280 / 0.140 / 0.076 / 0.039 +- 15 %)."""
+    a, b = 1.5, 0.1
+    prob, _ = P.gbm(a, b, 1.0, 1.0)
+    solver = pychastic.sde_solver.SDESolver()
+    for dt, target in zip([2 ** -4, 2 ** -5, 2 ** -6, 2 ** -7], [0.280, 0.140, 0.076, 0.039]):
+        solver.dt = dt
+        sol = solver.solve_many(prob, n_trajectories=250)
+        x, t, w = (np.asarray(sol[k])[:, -1].ravel() for k in ("solution_values", "time_values", "wiener_values"))
+        err = np.abs(prob.exact_solution(1.0, t, w) - x)
+        assert np.isclose(err.mean(), target, rtol=0.15)
+
+
+def test_strong_and_weak_orders_on_the_polar_walk():
+    """Strong error of the three schemes against the exact cartesian Brownian motion and the weak error of
+    E[phi_T] (reference examples/examples_from_paper/polar_random_walk.py:23: atan(2) = 1.10714532096375):
+    the scheme ranking and the decay with dt must hold on 2^17 fp64 trajectories."""
+    from stochastic_b200 import workloads
+    prob = workloads.polar_walk(4.0, (2.0, 0.0), 1.0, f64=True)
+    obs = workloads.polar_error_observables(4.0, 2.0)
+    n = 2 ** 17
+    med = {}
+    for scheme in ("euler", "milstein", "wagner_platen"):
+        for e in (5, 7):
+            solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=2.0 ** -e)
+            sol = solver.solve_many(prob, n_trajectories=n, seed=0, chunk_size=None)
+            x, w, t = (np.asarray(sol[k])[:, -1] for k in ("solution_values", "wiener_values", "time_values"))
+            ex = x[:, 0] * np.cos(x[:, 1]) - (w[:, 0] + 2.0)
+            ey = x[:, 0] * np.sin(x[:, 1]) - (w[:, 1] + 4.0 * t)
+            med[scheme, e] = np.median(np.hypot(ex, ey))
+    # measured on B200 (profiles/README.md): medians 4.1e-2 / 2.6e-2 / 8.3e-4 at dt=2^-7, slopes 0.77 / 1.01 / 1.53
+    assert med["milstein", 7] < 0.8 * med["euler", 7]
+    assert med["wagner_platen", 7] < 0.1 * med["milstein", 7]
+    for scheme, order in (("euler", 0.5), ("milstein", 1.0), ("wagner_platen", 1.5)):
+        slope = np.log2(med[scheme, 5] / med[scheme, 7]) / 2
+        assert slope > 0.8 * order, (scheme, slope)
+    solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=2.0 ** -6)
+    sol = solver.solve_many(prob, n_trajectories=n, seed=0, chunk_size=None, observables=obs)
+    mom = np.asarray(sol["moments"])
+    mean_phi = mom[1, 0] / n
+    sigma = np.sqrt(0.5951002076847987 / n)
+    assert abs(mean_phi - 1.10714532096375) < 5 * sigma + 2e-3
