@@ -64,6 +64,27 @@ typedef struct sdeb200_wiener_args {
     void* d_www;  /* (steps, m, m, m)  or NULL */
 } sdeb200_wiener_args_t;
 
+/* Mirrors sdeb::BeadArgs (stochastic_b200/csrc/sde_bead_kernel.cuh): Euler-Maruyama Brownian dynamics of a
+ * closed chain of N equal beads with RPY mobility, drift = mu (-grad U), noise = sqrt(2) chol(mu) - the built-in
+ * functor for reference examples/example_writhed_dna_loop.py:49-86 (stretch + bend + overlap energy). */
+typedef struct sdeb200_bead_args {
+    uint32_t key_a, key_b;
+    uint32_t n_fragments, cpr, chunk, n_snapshots;
+    uint64_t n_traj_total, traj_begin, traj_count;
+    const void* x0;          /* device (n_ic, 3N) working dtype */
+    int64_t x0_stride;       /* 0 = broadcast */
+    double dt;
+    double radius;           /* hydrodynamic radius of every bead */
+    double ks, d0;           /* stretch stiffness and rest length */
+    double kb_over_d04;      /* bending stiffness / d0^4 */
+    double ko;               /* overlap stiffness */
+    double sigma2;           /* steric diameter squared */
+    double inv_delta2;       /* 1 / (overlap smear width)^2 */
+    void* out_t;             /* device (traj_count, n_snapshots)      or NULL */
+    void* out_x;             /* device (traj_count, n_snapshots, 3N)  or NULL */
+    void* out_w;             /* device (traj_count, n_snapshots, 3N)  or NULL */
+} sdeb200_bead_args_t;
+
 int sdeb200_abi_version(void);
 const char* sdeb200_last_error(void);
 
@@ -90,6 +111,11 @@ int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, in
  * in-kernel normal generator). */
 int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block,
                   size_t dyn_smem_bytes, void* stream);
+
+/* Launch the bead-chain kernel (entry `sde_bead_kernel`): one CTA of `block` threads per trajectory, at most
+ * `max_ctas` CTAs (grid-stride over trajectories; 0 = one CTA per trajectory). */
+int sdeb200_bead_solve(sdeb200_program_t* prog, const sdeb200_bead_args_t* args, int block,
+                       size_t dyn_smem_bytes, unsigned max_ctas, void* stream);
 
 /* Launch the unit-step Wiener-integral generator kernel (one thread per step). */
 int sdeb200_wiener_integrals(sdeb200_program_t* prog, const sdeb200_wiener_args_t* args, int block,

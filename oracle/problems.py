@@ -138,3 +138,38 @@ def jfm_four_beads(tmax=8000.0, half=False):
     k = 5.5 * (0.5 if half else 1.0)
     return bead_chain([3.0, 1.0, 1.0, 1.0], [(0, 1, k, 4.0), (1, 2, k, 4.0), (2, 3, k, 4.0)],
                       [-2.0, 0, 0, 2.0, 0, 0, 6.0, 0, 0, 10.0, 0, 0], tmax, name="jfm_four_beads")
+
+
+def dna_loop(n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., steric_diameter=20.0 / 1111., kbT=1.0,
+             persistence_length=500.0 / 1111., stretch_length=0.037 / 1111., overlap_strength=70.0, tmax=6000.0e-6):
+    """reference `examples/example_writhed_dna_loop.py:25-84` without the twist term (pywrithe is unavailable):
+    energy written as in the example, differentiated by torch autograd."""
+    n = n_beads
+    d0 = beam_length / n
+    ks = kbT / (stretch_length * d0)
+    kb = kbT * persistence_length * d0
+    ko = overlap_strength * kbT
+    delta = 0.6 * steric_diameter
+    radii = torch.full((n,), hydrodynamic_diameter / 2.0, dtype=torch.float64)
+
+    def energy(x):
+        loc = x.reshape(n, 3)
+        dist = torch.sum((loc - torch.roll(loc, 1, 0)) ** 2, dim=1) ** 0.5
+        ext = ks * 0.5 * torch.sum((dist - d0) ** 2)
+        curv = torch.sum((loc - 2 * torch.roll(loc, 1, 0) + torch.roll(loc, 2, 0)) ** 2, dim=1) ** 0.5 / d0 ** 2
+        bend = kb * 0.5 * torch.sum(curv ** 2)
+        r2 = torch.sum((loc[:, None, :] - loc[None, :, :]) ** 2, dim=-1)
+        over = ko * (0.5 * torch.sum(torch.tanh((steric_diameter ** 2 - r2) / delta ** 2) + 1.0) - n)
+        return ext + bend + over
+
+    def a(x):
+        mu = rpy.muTT_torch(x.reshape(n, 3), radii.to(x.dtype))
+        return mu @ (-torch.func.grad(energy)(x))
+
+    def b(x):
+        mu = rpy.muTT_torch(x.reshape(n, 3), radii.to(x.dtype))
+        return (2 ** 0.5) * torch.linalg.cholesky(mu)
+
+    k = np.arange(n)
+    x0 = (beam_length / (2 * np.pi)) * np.stack([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), np.zeros(n)], 1)
+    return OracleProblem(a, b, x0.ravel(), tmax, name="dna_loop")

@@ -23,6 +23,7 @@
 
 static_assert(sizeof(sdeb200_solve_args_t) == 112, "sdeb200_solve_args_t layout");
 static_assert(sizeof(sdeb200_wiener_args_t) == 56, "sdeb200_wiener_args_t layout");
+static_assert(sizeof(sdeb200_bead_args_t) == 152, "sdeb200_bead_args_t layout");
 
 namespace {
 
@@ -221,6 +222,31 @@ int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int
     CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1,
                                        (unsigned)dyn_smem_bytes, (CUstream)stream, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_solve_kernel): " + cu_err(r));
+    return 0;
+}
+
+int sdeb200_bead_solve(sdeb200_program_t* prog, const sdeb200_bead_args_t* args, int block, size_t dyn_smem_bytes,
+                       unsigned max_ctas, void* stream) {
+    if (!prog || !args) return fail(-1, "sdeb200_bead_solve: null argument");
+    if (block <= 0 || block > 1024 || (block % 32)) return fail(-1, "sdeb200_bead_solve: bad block size");
+    if (args->traj_count == 0) return 0;
+    if (!args->x0) return fail(-1, "sdeb200_bead_solve: x0 is NULL");
+    if (args->traj_begin + args->traj_count > args->n_traj_total)
+        return fail(-1, "sdeb200_bead_solve: trajectory range exceeds n_traj_total");
+    if (args->n_fragments == 0 || args->cpr == 0 || args->chunk == 0)
+        return fail(-1, "sdeb200_bead_solve: n_fragments, cpr and chunk must be positive");
+    if ((uint64_t)args->n_snapshots > (uint64_t)args->n_fragments * args->cpr)
+        return fail(-1, "sdeb200_bead_solve: n_snapshots exceeds n_fragments * cpr");
+    if (!(args->dt > 0) || !(args->radius > 0)) return fail(-1, "sdeb200_bead_solve: dt and radius must be positive");
+    uint64_t grid = args->traj_count;
+    if (max_ctas && grid > max_ctas) grid = max_ctas;
+    if (grid > 0x7fffffffULL) grid = 0x7fffffffULL;
+    if (int e = ensure_smem(prog, dyn_smem_bytes)) return e;
+    sdeb200_bead_args_t a = *args;
+    void* params[] = {&a};
+    CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1,
+                                       (unsigned)dyn_smem_bytes, (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_bead_kernel): " + cu_err(r));
     return 0;
 }
 

@@ -18,7 +18,7 @@ CACHE_DIR = os.environ.get("SDEB200_CACHE_DIR", os.path.join(_HERE, "_cubin_cach
 EXPORTS = (
     "sdeb200_abi_version", "sdeb200_last_error", "sdeb200_set_device", "sdeb200_compile", "sdeb200_free",
     "sdeb200_program_load", "sdeb200_program_destroy", "sdeb200_program_info", "sdeb200_solve",
-    "sdeb200_wiener_integrals", "sdeb200_keys_split", "sdeb200_normal", "sdeb200_fp64_peak",
+    "sdeb200_wiener_integrals", "sdeb200_keys_split", "sdeb200_normal", "sdeb200_fp64_peak", "sdeb200_bead_solve",
 )
 
 
@@ -45,7 +45,22 @@ class WienerArgs(ctypes.Structure):
     ]
 
 
-assert ctypes.sizeof(SolveArgs) == 112 and ctypes.sizeof(WienerArgs) == 56
+class BeadArgs(ctypes.Structure):
+    """Mirror of `sdeb200_bead_args_t`."""
+    _fields_ = [
+        ("key_a", ctypes.c_uint32), ("key_b", ctypes.c_uint32),
+        ("n_fragments", ctypes.c_uint32), ("cpr", ctypes.c_uint32),
+        ("chunk", ctypes.c_uint32), ("n_snapshots", ctypes.c_uint32),
+        ("n_traj_total", ctypes.c_uint64), ("traj_begin", ctypes.c_uint64), ("traj_count", ctypes.c_uint64),
+        ("x0", ctypes.c_void_p), ("x0_stride", ctypes.c_int64),
+        ("dt", ctypes.c_double), ("radius", ctypes.c_double), ("ks", ctypes.c_double), ("d0", ctypes.c_double),
+        ("kb_over_d04", ctypes.c_double), ("ko", ctypes.c_double), ("sigma2", ctypes.c_double),
+        ("inv_delta2", ctypes.c_double),
+        ("out_t", ctypes.c_void_p), ("out_x", ctypes.c_void_p), ("out_w", ctypes.c_void_p),
+    ]
+
+
+assert ctypes.sizeof(SolveArgs) == 112 and ctypes.sizeof(WienerArgs) == 56 and ctypes.sizeof(BeadArgs) == 152
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -83,6 +98,8 @@ def lib():
                                     ctypes.c_void_p]
         L.sdeb200_wiener_integrals.argtypes = [ctypes.c_void_p, ctypes.POINTER(WienerArgs), ctypes.c_int,
                                                ctypes.c_size_t, ctypes.c_void_p]
+        L.sdeb200_bead_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(BeadArgs), ctypes.c_int, ctypes.c_size_t,
+                                         ctypes.c_uint, ctypes.c_void_p]
         L.sdeb200_keys_split.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.sdeb200_normal.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
@@ -157,7 +174,7 @@ def current_stream_ptr():
 # ------------------------------------------------------------------------------------------
 def _core_fingerprint():
     h = hashlib.sha256()
-    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_wiener_kernel.cuh"):
+    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_wiener_kernel.cuh", "sde_bead_kernel.cuh"):
         with open(os.path.join(CSRC_DIR, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()

@@ -82,6 +82,68 @@ def four_beads(tmax=8000.0, half_spring=False, f64=False):
                       [[-2.0, 0, 0], [2.0, 0, 0], [6.0, 0, 0], [10.0, 0, 0]], tmax, f64)
 
 
+class BeadRingProblem:
+    """Closed chain of N equal beads with RPY hydrodynamic interactions (the writhed-DNA-loop model of
+    reference `examples/example_writhed_dna_loop.py:25-84` without its twist/writhe term, whose dependency
+    `pywrithe` has neither source nor fixture).
+
+    Carries the same attributes as `SDEProblem` (`a`, `b`, `x0`, `tmax`, `dimension`, `noise_terms`) - `a` and
+    `b` are the reference's drift / noise written against `stochastic_b200.numpy`, usable by the generic traced
+    kernel for small N - plus `bead_ring`, the parameter block of the dedicated CTA-per-trajectory kernel
+    (csrc/sde_bead_kernel.cuh) that `SDESolver` dispatches to when the state is too large to trace (d > 24)."""
+
+    def __init__(self, n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., steric_diameter=20.0 / 1111.,
+                 kbT=1.0, persistence_length=500.0 / 1111., stretch_length=0.037 / 1111., overlap_strength=70.0,
+                 x0=None, tmax=6000.0e-6, f64=False):
+        n = int(n_beads)
+        d0 = beam_length / n
+        ks = kbT / (stretch_length * d0)
+        kb = kbT * persistence_length * d0
+        ko = overlap_strength * kbT
+        delta = 0.6 * steric_diameter
+        radius = hydrodynamic_diameter / 2.0
+        self.bead_ring = dict(n_beads=n, radius=radius, ks=ks, d0=d0, kb_over_d04=kb / d0 ** 4, ko=ko,
+                              sigma2=steric_diameter ** 2, inv_delta2=1.0 / delta ** 2)
+        radii = np.full(n, radius)
+
+        def u_ene(x):
+            loc = jnp.reshape(x, (n, 3))
+            dist = jnp.sum((loc - jnp.roll(loc, 1, axis=0)) ** 2, axis=1) ** 0.5
+            ext = ks * 0.5 * jnp.sum((dist - d0) ** 2)
+            curv2 = jnp.sum((loc - 2 * jnp.roll(loc, 1, axis=0) + jnp.roll(loc, 2, axis=0)) ** 2, axis=1) / d0 ** 4
+            bend = kb * 0.5 * jnp.sum(curv2)
+            diff = loc[:, None, :] - loc[None, :, :]
+            over = ko * (0.5 * jnp.sum(jnp.tanh((steric_diameter ** 2 - jnp.sum(diff ** 2, axis=-1)) / delta ** 2) + 1.0) - n)
+            return ext + bend + over
+
+        def drift(x):
+            mu = grpy.muTT(jnp.reshape(x, (n, 3)), radii)
+            return jnp.matmul(mu, -grad(u_ene)(x))
+
+        def noise(x):
+            mu = grpy.muTT(jnp.reshape(x, (n, 3)), radii)
+            return jnp.sqrt(2) * jnp.linalg.cholesky(mu)
+
+        self.u_ene, self.a, self.b = u_ene, drift, noise
+        if x0 is None:   # circle of circumference beam_length (reference :79-81)
+            k = np.arange(n)
+            x0 = (beam_length / (2 * np.pi)) * np.stack([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n),
+                                                        np.zeros(n)], axis=1)
+        self.x0 = np.asarray(x0, dtype=np.float64 if f64 else np.float32).reshape(-1)
+        if self.x0.size != 3 * n:
+            raise ValueError(f"Inconsistent shapes: x0 has {self.x0.size} entries, expected {3 * n}")
+        if not tmax > 0:
+            raise ValueError(f"tmax has to be positive, not {tmax}")
+        self.tmax = tmax
+        self.dimension = self.noise_terms = 3 * n
+        self.exact_solution = None
+
+
+def dna_loop(n_beads=40, tmax=6000.0e-6, f64=False, **kw):
+    """BASELINE config C4 (without the parity-unpinned twist term)."""
+    return BeadRingProblem(n_beads=n_beads, tmax=tmax, f64=f64, **kw)
+
+
 def call_payoff(strike=120.0):
     """European call payoff max(S_T - K, 0) as a device-side observable."""
     return lambda x, w, t: jnp.array([jnp.maximum(x[0] - strike, 0.0)])
