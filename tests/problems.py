@@ -74,3 +74,44 @@ def as_f64(problem, oracle_problem=None):
     src = problem.x0 if oracle_problem is None else np.asarray(oracle_problem.x0).reshape(np.shape(problem.x0))
     problem.x0 = np.asarray(src, dtype=np.float64)
     return problem
+
+
+def coupled_3x3():
+    """d = m = 3 test system with non-commutative noise (all Wagner-Platen tensors populated)."""
+    p = pychastic.sde_problem.SDEProblem(
+        a=lambda x: jnp.array([-0.5 * x[0] + 0.1 * x[1] * x[2], 0.3 * jnp.sin(x[0]) - 0.2 * x[1], 0.1 - 0.4 * x[2]]),
+        b=lambda x: jnp.array([[0.3 + 0.1 * x[1], 0.05 * x[2], 0.0],
+                               [0.1 * jnp.cos(x[0]), 0.2, 0.07 * x[0]],
+                               [0.0, 0.1 * x[0] * x[1], 0.25 + 0.05 * jnp.sin(x[2])]]),
+        x0=jnp.array([0.5, -0.25, 1.0]), tmax=0.5)
+    import torch
+    from oracle.solver import OracleProblem
+
+    def oa(x):
+        return torch.stack([-0.5 * x[0] + 0.1 * x[1] * x[2], 0.3 * torch.sin(x[0]) - 0.2 * x[1], 0.1 - 0.4 * x[2]])
+
+    def ob(x):
+        z = 0 * x[0]
+        return torch.stack([torch.stack([0.3 + 0.1 * x[1], 0.05 * x[2], z]),
+                            torch.stack([0.1 * torch.cos(x[0]), 0.2 + z, 0.07 * x[0]]),
+                            torch.stack([z, 0.1 * x[0] * x[1], 0.25 + 0.05 * torch.sin(x[2])])])
+    return p, OracleProblem(oa, ob, [0.5, -0.25, 1.0], 0.5, name="coupled_3x3")
+
+
+def rectangular_2x3():
+    """d = 2, m = 3 (more noise terms than dimensions)."""
+    p = pychastic.sde_problem.SDEProblem(
+        a=lambda x: jnp.array([0.1 * x[1], -0.2 * x[0]]),
+        b=lambda x: jnp.array([[0.2, 0.1 * x[1], 0.05 * x[0] * x[1]], [0.1 * x[0], 0.3, 0.02]]),
+        x0=jnp.array([1.0, 0.5]), tmax=0.5)
+    import torch
+    from oracle.solver import OracleProblem
+
+    def oa(x):
+        return torch.stack([0.1 * x[1], -0.2 * x[0]])
+
+    def ob(x):
+        z = 0 * x[0]
+        return torch.stack([torch.stack([0.2 + z, 0.1 * x[1], 0.05 * x[0] * x[1]]),
+                            torch.stack([0.1 * x[0], 0.3 + z, 0.02 + z])])
+    return p, OracleProblem(oa, ob, [1.0, 0.5], 0.5, name="rectangular_2x3")

@@ -1,0 +1,124 @@
+"""GPU parity, part 2: larger noise dimension, the partitionable PRNG layout, ragged sizes for the staged
+snapshot stores, prefixes of long runs, empty runs, device-side moments and the result-array surface."""
+import numpy as np
+import pytest
+import torch
+
+import stochastic_b200 as pychastic
+import stochastic_b200.numpy as jnp
+from stochastic_b200 import workloads
+from oracle import solver as osolver
+
+import problems as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _close64(got, ref, rtol=1e-9):
+    for k in ("time_values", "solution_values", "wiener_values"):
+        g, r = np.asarray(got[k]), ref[k]
+        assert g.shape == r.shape, (k, g.shape, r.shape)
+        err = np.abs(g - r) / np.maximum(np.abs(r), 1e-3)
+        assert err.max() < rtol, (k, err.max())
+
+
+@pytest.mark.parametrize("scheme", ["euler", "milstein", "wagner_platen"])
+@pytest.mark.parametrize("name", ["coupled_3x3", "rectangular_2x3"])
+def test_three_noise_terms(name, scheme):
+    prob, oprob = getattr(P, name)()
+    P.as_f64(prob, oprob)
+    solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=prob.tmax / 8)
+    got = solver.solve_many(prob, n_trajectories=9, seed=11, chunk_size=2)
+    ref = osolver.solve_many(oprob, scheme=scheme, dt=prob.tmax / 8, n_trajectories=9, seed=11, chunk_size=2,
+                             dtype=np.float64)
+    _close64(got, ref)
+
+
+@pytest.mark.parametrize("scheme", ["euler", "milstein", "wagner_platen"])
+def test_partitionable_layout(scheme):
+    """jax >= 0.5 default key / bit layout (jax_threefry_partitionable=True)."""
+    prob, oprob = P.polar_walk(4.0, (2.0, 0.0), 0.25)
+    P.as_f64(prob, oprob)
+    solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=2 ** -5)
+    got = solver.solve_many(prob, n_trajectories=10, seed=6, chunks_per_randomization=2, prng_layout="partitionable")
+    ref = osolver.solve_many(oprob, scheme=scheme, dt=2 ** -5, n_trajectories=10, seed=6, chunks_per_randomization=2,
+                             dtype=np.float64, layout="partitionable")
+    _close64(got, ref)
+    other = solver.solve_many(prob, n_trajectories=10, seed=6, chunks_per_randomization=2)
+    assert not np.allclose(np.asarray(other["wiener_values"]), ref["wiener_values"])
+
+
+@pytest.mark.parametrize("n_traj,steps,chunk", [(45, 23, 1), (33, 37, 2), (1, 16, 1), (70, 5, 1), (64, 40, 3)])
+def test_ragged_sizes_through_the_staged_snapshot_stores(n_traj, steps, chunk):
+    """Trajectory counts that are not multiples of the warp size and snapshot counts that are not multiples of the
+    staging tile (SDE_SNAP_TILE = 16)."""
+    prob, oprob = P.gbm(0.2, 0.5, 1.0, 1.0)
+    P.as_f64(prob, oprob)
+    for scheme in ("euler", "wagner_platen"):
+        solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=1.0 / steps)
+        got = solver.solve_many(prob, n_trajectories=n_traj, seed=2, chunk_size=chunk)
+        ref = osolver.solve_many(oprob, scheme=scheme, dt=1.0 / steps, n_trajectories=n_traj, seed=2, chunk_size=chunk,
+                                 dtype=np.float64, use_closed_form=True)
+        _close64(got, ref)
+
+
+def test_staged_stores_for_vector_state_and_multiple_ics():
+    prob, oprob = P.polar_walk(0.0, (1.0, 0.0), 1.0)
+    x0 = np.array([[1.0, 0.0], [2.0, 0.5], [1.5, -0.3], [3.0, 1.0], [0.8, 2.0]])
+    prob.x0 = x0
+    oprob.x0 = x0
+    solver = pychastic.sde_solver.SDESolver(scheme="milstein", dt=1 / 40)
+    got = solver.solve_many(prob, n_trajectories=None, seed=9)
+    ref = osolver.solve_many(oprob, scheme="milstein", dt=1 / 40, n_trajectories=None, seed=9, dtype=np.float64)
+    assert np.asarray(got["solution_values"]).shape == (5, 40, 2)
+    _close64(got, ref)
+
+
+def test_max_snapshots_is_a_prefix_of_the_full_run():
+    prob, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    P.as_f64(prob)
+    solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=1 / 64)
+    full = solver.solve_many(prob, n_trajectories=20, seed=1, chunk_size=4, chunks_per_randomization=2)
+    head = solver.solve_many(prob, n_trajectories=20, seed=1, chunk_size=4, chunks_per_randomization=2, max_snapshots=5)
+    for k in ("time_values", "solution_values", "wiener_values"):
+        assert np.array_equal(np.asarray(full[k])[:, :5], np.asarray(head[k]))
+
+
+def test_empty_run():
+    prob, _ = P.gbm()
+    sol = pychastic.sde_solver.SDESolver(dt=0.25).solve_many(prob, n_trajectories=0)
+    assert np.asarray(sol["solution_values"]).shape == (0, 8, 1)
+
+
+def test_call_payoff_moments_match_oracle():
+    """BASELINE config 5 in miniature: GARCH model, call payoff reduced on the device."""
+    prob, oprob = P.garch(tmax=0.5)
+    P.as_f64(prob, oprob)
+    solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=0.05)
+    got = solver.solve_many(prob, n_trajectories=300, seed=4, chunk_size=None, observables=workloads.call_payoff(100.0),
+                            store_trajectories=False)
+    assert "solution_values" not in got
+    ref = osolver.solve_many(oprob, scheme="wagner_platen", dt=0.05, n_trajectories=300, seed=4, chunk_size=None,
+                             dtype=np.float64)
+    payoff = np.maximum(ref["solution_values"][:, -1, 0] - 100.0, 0.0)
+    mom = np.asarray(got["moments"])
+    assert got["count"] == 300
+    assert np.isclose(mom[0, 0], payoff.sum(), rtol=1e-9) and np.isclose(mom[0, 1], (payoff ** 2).sum(), rtol=1e-9)
+
+
+def test_result_arrays_behave_like_numpy_and_export_dlpack():
+    prob, _ = P.gbm()
+    sol = pychastic.sde_solver.SDESolver(dt=0.125).solve_many(prob, n_trajectories=6, seed=0)
+    x = sol["solution_values"]
+    x.block_until_ready()
+    assert x.shape == (6, 16, 1) and x.ndim == 3 and x.dtype == np.float32 and len(x) == 6
+    host = np.asarray(x)
+    assert np.array_equal(np.asarray(x[:, -1]), host[:, -1])
+    assert np.array_equal(np.asarray(x[2:4, ::2, 0]), host[2:4, ::2, 0])
+    assert np.allclose(np.asarray(x.reshape(-1, 1)), host.reshape(-1, 1))
+    assert np.isclose(float(jnp.mean(x)), host.mean()) and np.isclose(float(x.mean()), host.mean())
+    assert np.allclose(np.asarray(2.0 * x + 1.0), 2.0 * host + 1.0)
+    t = torch.from_dlpack(x)
+    assert t.is_cuda and t.data_ptr() == x.torch().data_ptr()
+    (r,) = np.asarray(x[:, -1, :]).transpose()
+    assert r.shape == (6,)
