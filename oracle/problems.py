@@ -173,3 +173,49 @@ def dna_loop(n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., st
     k = np.arange(n)
     x0 = (beam_length / (2 * np.pi)) * np.stack([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), np.zeros(n)], 1)
     return OracleProblem(a, b, x0.ravel(), tmax, name="dna_loop")
+
+
+def brownian_rotations(tmax=20.0):
+    """reference `examples/examples_from_paper/brownian_rotations.py:7-86` with `jax.lax.cond` written as
+    `torch.where` (what vmap turns it into).  Returns (problem, canonicalize_coordinates on numpy batches)."""
+    mobility = 2.0 * torch.eye(3, dtype=torch.float64)
+    mobility_d = torch.linalg.cholesky(mobility)
+    eye = torch.eye(3, dtype=torch.float64)
+
+    def spin(q):
+        z = 0 * q[0]
+        return torch.stack([torch.stack([z, -q[2], q[1]]), torch.stack([q[2], z, -q[0]]), torch.stack([-q[1], q[0], z])])
+
+    def rotation_matrix(q):
+        phi = torch.sqrt(torch.sum(q ** 2))
+        rot = ((torch.sin(phi) / phi) * spin(q) + torch.cos(phi) * eye.to(q.dtype)
+               + ((1.0 - torch.cos(phi)) / phi ** 2) * q.reshape(1, 3) * q.reshape(3, 1))
+        return torch.where(phi > 0.01, rot, eye.to(q.dtype))
+
+    def transformation_matrix(q):
+        phi = torch.sqrt(torch.sum(q ** 2))
+        trans = (0.5 * (1.0 / phi ** 2 - (torch.sin(phi) / (2.0 * phi * (1.0 - torch.cos(phi))))) * q.reshape(1, 3)
+                 * q.reshape(3, 1) + spin(q) + (phi * torch.sin(phi) / (1.0 - torch.cos(phi))) * eye.to(q.dtype))
+        return torch.where(phi > 0.01, trans, eye.to(q.dtype))
+
+    def metric_force(q):
+        phi = torch.sqrt(torch.sum(q ** 2))
+        scale = torch.where(phi < 0.01, -phi / 6.0, torch.sin(phi) / (1.0 - torch.cos(phi)) - 2.0 / phi)
+        return torch.where(phi > 0.0, (q / phi) * scale, torch.zeros(3, dtype=q.dtype))
+
+    def t_mobility(q):
+        T = transformation_matrix(q)
+        return T @ mobility.to(q.dtype) @ T.T
+
+    def drift(q):
+        return t_mobility(q) @ metric_force(q) + torch.einsum("iji->j", torch.func.jacfwd(t_mobility)(q))
+
+    def noise(q):
+        return (2 ** 0.5) * transformation_matrix(q) @ rotation_matrix(q).T @ mobility_d.to(q.dtype)
+
+    def canonicalize(x):
+        phi = np.sqrt(np.sum(x ** 2, axis=-1, keepdims=True))
+        canonical = np.fmod(phi + np.pi, 2 * np.pi) - np.pi
+        return np.where(phi > np.pi, (canonical / phi) * x, x)
+
+    return OracleProblem(drift, noise, [1.0, 0.0, 0.0], tmax, name="brownian_rotations"), canonicalize

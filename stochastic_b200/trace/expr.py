@@ -78,23 +78,32 @@ class Expr:
         raise TypeError("traced quantity has no concrete value")
 
     # -- operators ------------------------------------------------------------------------
-    def __add__(self, o): return add(self, o)
-    def __radd__(self, o): return add(o, self)
-    def __sub__(self, o): return sub(self, o)
-    def __rsub__(self, o): return sub(o, self)
-    def __mul__(self, o): return mul(self, o)
-    def __rmul__(self, o): return mul(o, self)
-    def __truediv__(self, o): return div(self, o)
-    def __rtruediv__(self, o): return div(o, self)
-    def __pow__(self, o): return power(self, o)
-    def __rpow__(self, o): return power(o, self)
+    # (scalar op array) broadcasts over the array: numpy defers to us because __array_ufunc__ is None
+    def _bin(self, o, fn, reverse=False):
+        if isinstance(o, np.ndarray) and o.ndim > 0:
+            f = (lambda v: fn(wrap(v), self)) if reverse else (lambda v: fn(self, wrap(v)))
+            out = np.frompyfunc(f, 1, 1)(np.asarray(o, dtype=object))
+            from .. import jnp
+            return out.view(jnp.TArray)
+        return fn(o, self) if reverse else fn(self, o)
+
+    def __add__(self, o): return self._bin(o, add)
+    def __radd__(self, o): return self._bin(o, add, True)
+    def __sub__(self, o): return self._bin(o, sub)
+    def __rsub__(self, o): return self._bin(o, sub, True)
+    def __mul__(self, o): return self._bin(o, mul)
+    def __rmul__(self, o): return self._bin(o, mul, True)
+    def __truediv__(self, o): return self._bin(o, div)
+    def __rtruediv__(self, o): return self._bin(o, div, True)
+    def __pow__(self, o): return self._bin(o, power)
+    def __rpow__(self, o): return self._bin(o, power, True)
     def __neg__(self): return neg(self)
     def __pos__(self): return self
     def __abs__(self): return unary("abs", self)
-    def __lt__(self, o): return binary("lt", self, o)
-    def __le__(self, o): return binary("le", self, o)
-    def __gt__(self, o): return binary("gt", self, o)
-    def __ge__(self, o): return binary("ge", self, o)
+    def __lt__(self, o): return self._bin(o, lambda a, b: binary("lt", a, b))
+    def __le__(self, o): return self._bin(o, lambda a, b: binary("le", a, b))
+    def __gt__(self, o): return self._bin(o, lambda a, b: binary("gt", a, b))
+    def __ge__(self, o): return self._bin(o, lambda a, b: binary("ge", a, b))
     def __eq__(self, o):
         if isinstance(o, Expr) or _is_number(o):
             return binary("eq", self, o)

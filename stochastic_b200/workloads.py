@@ -180,3 +180,52 @@ def precompile_all():
         SDESolver(scheme=scheme).compile(prob, observables=obs)
         n += 1
     return n
+
+
+def brownian_rotations(tmax=20.0, f64=False):
+    """Rotational Brownian motion on SO(3) in rotation-vector coordinates (Evensen et al. 2008), the
+    `step_post_processing` showcase of the reference (`examples/examples_from_paper/brownian_rotations.py:7-93`).
+    Returns (problem, canonicalize_coordinates)."""
+    from . import lax
+    from .autodiff import jacobian
+    mobility = 2.0 * np.eye(3)
+    mobility_d = np.linalg.cholesky(mobility)
+
+    def spin_matrix(q):
+        return jnp.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]])
+
+    def rotation_matrix(q):
+        phi = jnp.sqrt(jnp.sum(q ** 2))
+        rot = ((jnp.sin(phi) / phi) * spin_matrix(q) + jnp.cos(phi) * jnp.eye(3)
+               + ((1.0 - jnp.cos(phi)) / phi ** 2) * q.reshape(1, 3) * q.reshape(3, 1))
+        return lax.cond(phi > 0.01, lambda: rot, lambda: 1.0 * jnp.eye(3))
+
+    def transformation_matrix(q):
+        phi = jnp.sqrt(jnp.sum(q ** 2))
+        trans = (0.5 * (1.0 / phi ** 2 - (jnp.sin(phi) / (2.0 * phi * (1.0 - jnp.cos(phi))))) * q.reshape(1, 3)
+                 * q.reshape(3, 1) + spin_matrix(q) + (phi * jnp.sin(phi) / (1.0 - jnp.cos(phi))) * jnp.eye(3))
+        return lax.cond(phi > 0.01, lambda: trans, lambda: 1.0 * jnp.eye(3))
+
+    def metric_force(q):
+        phi = jnp.sqrt(jnp.sum(q ** 2))
+        scale = lax.cond(phi < 0.01, lambda t: -t / 6.0, lambda t: jnp.sin(t) / (1.0 - jnp.cos(t)) - 2.0 / t, phi)
+        return lax.cond(phi > 0.0, lambda: (q / phi) * scale, lambda: jnp.array([0.0, 0.0, 0.0]))
+
+    def t_mobility(q):
+        return transformation_matrix(q) @ mobility @ (transformation_matrix(q).T)
+
+    def drift(q):
+        return t_mobility(q) @ metric_force(q) + jnp.einsum("iji->j", jacobian(t_mobility)(q))
+
+    def noise(q):
+        return jnp.sqrt(2) * transformation_matrix(q) @ (rotation_matrix(q).T) @ mobility_d
+
+    def canonicalize_coordinates(q):
+        phi = jnp.sqrt(jnp.sum(q ** 2))
+        max_phi = jnp.pi
+        canonical_phi = jnp.fmod(phi + max_phi, 2.0 * max_phi) - max_phi
+        return lax.cond(phi > max_phi, lambda canonical_phi, phi, q: (canonical_phi / phi) * q,
+                        lambda canonical_phi, phi, q: q, canonical_phi, phi, q)
+
+    p = SDEProblem(drift, noise, tmax=tmax, x0=jnp.array([1.0, 0.0, 0.0]))
+    return _finish(p, f64, [1.0, 0.0, 0.0]), canonicalize_coordinates

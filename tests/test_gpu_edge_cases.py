@@ -122,3 +122,19 @@ def test_result_arrays_behave_like_numpy_and_export_dlpack():
     assert t.is_cuda and t.data_ptr() == x.torch().data_ptr()
     (r,) = np.asarray(x[:, -1, :]).transpose()
     assert r.shape == (6,)
+
+
+def test_brownian_rotations_with_step_post_processing():
+    """the SO(3) rotational-diffusion example (lax.cond branches, jacobian inside the drift,
+    canonicalisation hook after every step), reference examples/examples_from_paper/brownian_rotations.py."""
+    from oracle import problems as oprob
+    prob, post = workloads.brownian_rotations(tmax=2.0, f64=True)
+    oracle_prob, opost = oprob.brownian_rotations(tmax=2.0)
+    solver = pychastic.sde_solver.SDESolver(dt=0.01)
+    got = solver.solve_many(prob, step_post_processing=post, n_trajectories=24, chunk_size=50,
+                            chunks_per_randomization=1, seed=3)
+    ref = osolver.solve_many(oracle_prob, scheme="euler", dt=0.01, n_trajectories=24, chunk_size=50,
+                             chunks_per_randomization=1, seed=3, dtype=np.float64, step_post_processing=opost)
+    _close64(got, ref, rtol=1e-7)          # 200 chaotic steps near the coordinate singularity amplify rounding
+    angles = np.sqrt((np.asarray(got["solution_values"]) ** 2).sum(-1))
+    assert angles.max() <= np.pi + 1e-9
