@@ -36,7 +36,11 @@ DT_EXPONENTS = list(range(1, 10))
 N_TRAJ_PER_GPU = 10 ** 7
 TMAX = 1.0
 Y_DRIFT = 4.0
-FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10)
+FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10): the contract (algorithmic) figure
+# ncu counters of the dominant launch (10^7 trajectories x 512 steps), profiles/r1_ncu_c2_bench_kernel_counters.csv:
+# DFMA 3703, DMUL 664, DADD 364 thread-instructions per trajectory-step; DRAM 42 MB read + 1961 MB written per launch
+EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3703 + 664 + 364
+DRAM_BYTES_PER_DOMINANT_LAUNCH = 41932288 + 1960619776
 THEORETICAL_MEAN_PHI = 1.10714532096375
 
 
@@ -265,6 +269,16 @@ def run_b200(args):
     d2h = sum(t.numel() * 8 for t in host_out) * len(DT_EXPONENTS) + 9 * 2 * 2 * 8
     h2d = 16 * len(DT_EXPONENTS)
 
+    # robust accuracy summary (outside every timed region): median strong error per dt from the final states
+    medians = []
+    for e in DT_EXPONENTS:
+        sol = solvers[e].solve_many(problem, n_trajectories=n_total, seed=0, chunk_size=None, progress_bar=False,
+                                    traj_range=(begin, min(n_local, 1 << 20)))
+        x, w, tt = (sol[k].torch()[:, -1] for k in ("solution_values", "wiener_values", "time_values"))
+        ex = x[:, 0] * torch.cos(x[:, 1]) - (w[:, 0] + 2.0)
+        ey = x[:, 0] * torch.sin(x[:, 1]) - (w[:, 1] + Y_DRIFT * tt)
+        medians.append(float(torch.median(torch.hypot(ex, ey)).item()))
+
     if rank == 0:
         mom = moments.cpu().numpy()
         n_all = float(n_total)
@@ -284,14 +298,26 @@ def run_b200(args):
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                             "frac": achieved / fp64_peak, "traffic": None,
+                             "frac": achieved / fp64_peak,
+                             "traffic": DRAM_BYTES_PER_DOMINANT_LAUNCH if n_local == N_TRAJ_PER_GPU else None,
+                             "traffic_note": "dram__bytes_read+write of this launch from ncu (round-1 capture, "
+                                             "profiles/r1_ncu_c2_bench_kernel_counters.csv); algorithmic bytes are the "
+                                             "400 MB of final states - the kernel is FP64/issue-bound, not HBM-bound",
+                             "executed_tflops": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12,
+                             "executed_frac": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12 / fp64_peak,
+                             "executed_note": "FP64 flops actually executed per trajectory-step (ncu DFMA x2 + DMUL + DADD "
+                                              "= 8434): the D/C-matrix factorisation does less work than the algorithmic "
+                                              "count, so both fractions are reported",
                              "kernel": "sde_solve_kernel (dt=2^-9 launch)", "kernel_ms": ms_k,
                              "flops_per_trajectory_step": FLOPS_PER_TRAJ_STEP,
                              "peak_source": "sdeb200_fp64_peak: DFMA loop measured in this run "
                                             "(MEASURED_PEAKS.json has no FP64 entry)"},
                 "cpu_baseline": cpu,
-                "accuracy": {"dt": [2.0 ** -e for e in DT_EXPONENTS], "mean_strong_error": strong,
-                             "weak_error_mean_phi": weak},
+                "accuracy": {"dt": [2.0 ** -e for e in DT_EXPONENTS], "median_strong_error": medians,
+                             "mean_strong_error": strong, "weak_error_mean_phi": weak,
+                             "note": "strong error = |cartesian(x_T) - exact Brownian path|; the mean is dominated by "
+                                     "the rare trajectories that step across the r = 0 coordinate singularity (as in "
+                                     "the reference), the median (first 2^20 trajectories of rank 0) shows the order"},
                 "kernel_registers": solvers[e].last_program.info()["registers"]}
         print(json.dumps(line), flush=True)
     if world > 1:
