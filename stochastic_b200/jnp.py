@@ -88,6 +88,8 @@ def _host(x):
     """Concrete value -> numpy (DeviceArray and torch tensors are copied to the host)."""
     if hasattr(x, "__sdeb200_host__"):
         return x.__sdeb200_host__()
+    if type(x).__module__.startswith("torch") and hasattr(x, "detach"):
+        return x.detach().cpu().numpy()          # torch tensors (any device) are accepted wherever arrays are
     if isinstance(x, (list, tuple)):
         return type(x)(_host(v) for v in x)
     return x

@@ -141,6 +141,16 @@ def _is_number(x):
     return isinstance(x, (int, float, bool, np.integer, np.floating, np.bool_))
 
 
+def trim_table(max_nodes=2_000_000):
+    """Bound the hash-consing table between traces: beyond `max_nodes` entries everything except constants and
+    variables is forgotten.  Nodes still referenced elsewhere stay valid; they merely stop being shared with
+    nodes built later (sharing is an optimisation, never a correctness requirement)."""
+    if len(_TABLE) > max_nodes:
+        keep = {k: v for k, v in _TABLE.items() if k[0] in ("const", "var")}
+        _TABLE.clear()
+        _TABLE.update(keep)
+
+
 def const(v):
     if isinstance(v, (bool, np.bool_)):
         return Expr._make("const", (), bool(v))

@@ -251,3 +251,55 @@ def test_wiener_integral_moments_known_values():
     assert np.isclose(wim.E2([1, 0], [0, 1])(1), 1 / 6)
     assert np.isclose(wim.E2([1, 2, 1])(1), 1 / 6) and wim.E2([1, 2, 1], [2, 1, 1])(1) == 0
     assert np.isclose(wim.E2([1], [1, 0])(2.0), 2.0)      # t^2 / 2
+
+
+# -- error behaviour of solve_many before any device work ----------------------------------------------------
+def test_shape_mismatch_asserts_like_the_reference():
+    """reference sde_solver.py:151-152: AssertionError when a(x0) / b(x0) do not match x0."""
+    prob = workloads.gbm()
+    prob.a = lambda x: jnp.zeros(3)
+    with pytest.raises(AssertionError):
+        pychastic.sde_solver.SDESolver().solve_many(prob, 2)
+
+
+def test_multiple_initial_conditions_reject_n_trajectories():
+    prob = workloads.gbm()
+    prob.x0 = jnp.tile(prob.x0, (4, 1))
+    with pytest.raises(ValueError):
+        pychastic.sde_solver.SDESolver().solve_many(prob, n_trajectories=1)
+
+
+def test_torch_tensors_are_accepted_as_initial_conditions():
+    p = pychastic.sde_problem.SDEProblem(lambda x: -x, lambda x: jnp.eye(2), torch.tensor([1.0, 2.0]), 1.0)
+    assert p.x0.tolist() == [1.0, 2.0] and p.dimension == 2
+
+
+def test_lax_cond_traces_both_branches():
+    from stochastic_b200 import lax
+    x = jnp.symbols((1,))
+    y = lax.cond(x[0] > 0.0, lambda v: v * 2.0, lambda v: -v, x[0])
+    vals = E.evaluate([E.wrap(y)], np.array([[3.0], [-4.0]]))[0]
+    assert vals.tolist() == [6.0, 4.0]
+    assert lax.cond(True, lambda: 1.0, lambda: 2.0) == 1.0
+
+
+def test_bead_ring_problem_host_side():
+    prob = workloads.dna_loop(n_beads=40)
+    assert prob.dimension == prob.noise_terms == 120 and prob.x0.dtype == np.float32
+    par = prob.bead_ring
+    assert np.isclose(par["d0"], 0.025) and np.isclose(par["ks"], 1.0 / ((0.037 / 1111.) * 0.025))
+    assert np.isclose(np.linalg.norm(prob.x0[:3] - prob.x0[3:6]), 2 * (1 / (2 * np.pi)) * np.sin(np.pi / 40))
+    small = workloads.dna_loop(n_beads=4, beam_length=0.1)
+    a = small.a(np.asarray(small.x0, dtype=np.float64))
+    b = small.b(np.asarray(small.x0, dtype=np.float64))
+    assert a.shape == (12,) and b.shape == (12, 12) and np.allclose(b, np.tril(b))
+    with pytest.raises(ValueError):
+        workloads.BeadRingProblem(n_beads=4, x0=np.zeros(5))
+
+
+def test_snapshot_tile_and_block_selection():
+    from stochastic_b200 import runtime
+    assert runtime.pick_snap_tile(1, 1, 128, True, 0, 512) == 16
+    assert runtime.pick_snap_tile(1, 1, 128, True, 0, 1) == 1 and runtime.pick_snap_tile(1, 1, 128, True, 0, 5) == 4
+    assert runtime.pick_snap_tile(2, 2, 256, True, 46 * 256 * 8, 128) == 1      # no room next to the normals staging
+    assert runtime.snap_tile_bytes(1, 1, 128, True, 16) == 4 * 3 * 16 * 33 * 8
