@@ -15,6 +15,7 @@ import sys as _sys
 from . import config  # noqa: F401
 from . import jnp  # noqa: F401
 from . import lax  # noqa: F401
+from . import prng  # noqa: F401
 from . import autodiff  # noqa: F401
 from . import sde_problem  # noqa: F401
 from . import sde_solver  # noqa: F401

@@ -42,16 +42,30 @@ def mean_and_stderr(moments, count):
     return mean, torch.sqrt(var / count)
 
 
-def solve_many_sharded(solver, problem, n_trajectories, observables=None, group=None, **kwargs):
+def solve_many_sharded(solver, problem, n_trajectories, observables=None, group=None, key_mode="global", seed=0,
+                       **kwargs):
     """`solver.solve_many` on this rank's shard of an n_trajectories-wide run.
+
+    key_mode="global" (default): every rank uses its slice of the GLOBAL fan-out split(PRNGKey(seed), N) - the
+    union of the shards is bit-identical to a single-process solve_many(n_trajectories=N).
+    key_mode="fold_in": rank r runs an independent count_r-trajectory solve keyed by
+    fold_in(PRNGKey(seed), r) - the scheme BASELINE.json's north_star names; a different (equally valid) stream,
+    with no limit on the global trajectory count.
 
     Returns the rank-local solution dict; if `observables` is given its 'moments' / 'count' entries hold the
     GLOBAL sums after one allreduce."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     begin, count = shard_range(n_trajectories, rank, world)
-    sol = solver.solve_many(problem, n_trajectories=n_trajectories, observables=observables,
-                            traj_range=(begin, count), **kwargs)
+    if key_mode == "global":
+        sol = solver.solve_many(problem, n_trajectories=n_trajectories, observables=observables, seed=seed,
+                                traj_range=(begin, count), **kwargs)
+    elif key_mode == "fold_in":
+        from . import prng
+        sol = solver.solve_many(problem, n_trajectories=count, observables=observables,
+                                seed=prng.fold_in(prng.PRNGKey(seed), rank), **kwargs)
+    else:
+        raise ValueError(f"unknown key_mode {key_mode!r}")
     sol["traj_range"] = (begin, count)
     if observables is not None:
         mom, total = allreduce_moments(sol["moments"].torch(), sol["count"], group)

@@ -303,3 +303,16 @@ def test_snapshot_tile_and_block_selection():
     assert runtime.pick_snap_tile(1, 1, 128, True, 0, 1) == 1 and runtime.pick_snap_tile(1, 1, 128, True, 0, 5) == 4
     assert runtime.pick_snap_tile(2, 2, 256, True, 46 * 256 * 8, 128) == 1      # no room next to the normals staging
     assert runtime.snap_tile_bytes(1, 1, 128, True, 16) == 4 * 3 * 16 * 33 * 8
+
+
+def test_host_prng_matches_oracle():
+    from stochastic_b200 import prng
+    from oracle import jax_prng
+    assert prng.threefry2x32((0x13198A2E, 0x03707344), 0x243F6A88, 0x85A308D3) == (0xC4923A9C, 0x483DF7A0)
+    assert prng.fold_in(prng.PRNGKey(0), 1) == (928981903, 3453687069)
+    for seed, n in [(0, 5), (7, 1), (123456789012, 4)]:
+        for layout in ("original", "partitionable"):
+            assert prng.split(prng.PRNGKey(seed), n, layout) == [tuple(int(v) for v in k) for k in
+                                                                 jax_prng.split(jax_prng.PRNGKey(seed), n, layout)]
+    from stochastic_b200.sde_solver import prng_key
+    assert prng_key(5) == (0, 5) and prng_key((3, 4)) == (3, 4) and prng_key(1 << 33) == (2, 0)
