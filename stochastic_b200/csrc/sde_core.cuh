@@ -565,22 +565,27 @@ struct WienerGen {
         // dependent threefry rounds / Horner chains with only two resident warps per scheduler.
         {
             const u32 base = s * (u32)(P * M), size = S * (u32)(P * M);
+#ifndef SDE_NORMAL_ROWS
+#define SDE_NORMAL_ROWS 1          // series terms r generated together (2M normals each)
+#endif
+            static_assert(P % SDE_NORMAL_ROWS == 0, "SDE_P must be a multiple of SDE_NORMAL_ROWS");
 #pragma unroll 1
-            for (int r = 0; r < P; ++r) {
-                Key kk[2 * M];
-                u32 ee[2 * M], ss[2 * M];
-                real nn[2 * M];
+            for (int r = 0; r < P; r += SDE_NORMAL_ROWS) {
+                constexpr int G = SDE_NORMAL_ROWS * M;
+                Key kk[2 * G];
+                u32 ee[2 * G], ss[2 * G];
+                real nn[2 * G];
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    kk[j] = k_zeta; kk[M + j] = k_eta;
-                    ee[j] = ee[M + j] = base + r * M + j;
-                    ss[j] = ss[M + j] = size;
+                for (int q = 0; q < G; ++q) {
+                    kk[q] = k_zeta; kk[G + q] = k_eta;
+                    ee[q] = ee[G + q] = base + r * M + q;
+                    ss[q] = ss[G + q] = size;
                 }
-                normal_group<2 * M>(kk, ee, ss, nn);
+                normal_group<2 * G>(kk, ee, ss, nn);
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    SDE_STAGE(r * M + j) = nn[j];
-                    SDE_STAGE(P * M + r * M + j) = nn[M + j];
+                for (int q = 0; q < G; ++q) {
+                    SDE_STAGE(r * M + q) = nn[q];
+                    SDE_STAGE(P * M + r * M + q) = nn[G + q];
                 }
             }
 #pragma unroll 1
