@@ -105,11 +105,11 @@ int sdeb200_program_destroy(sdeb200_program_t* prog);
 /* Registers per thread / static shared memory of the loaded kernel (diagnostics). */
 int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, int* max_threads);
 
-/* Launch the stepping kernel: one thread per trajectory, `block` threads per CTA
- * (must equal the SDE_BLOCK the program was compiled with), `dyn_smem_bytes` of dynamic shared
- * memory (SDE_STAGE_COUNT * SDE_BLOCK * sizeof(real): the per-thread staging columns of the
- * in-kernel normal generator). */
-int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block,
+/* Launch the stepping kernel: `block` threads per CTA (must equal the SDE_BLOCK the program was compiled
+ * with), `traj_per_block` trajectories per CTA (0 = block: one thread per trajectory; 128 for the
+ * warp-specialised variant whose 384-thread CTAs hold 128 consumer + 256 producer threads),
+ * `dyn_smem_bytes` of dynamic shared memory (the staging area of the in-kernel normal generator). */
+int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, int traj_per_block,
                   size_t dyn_smem_bytes, void* stream);
 
 /* Launch the bead-chain kernel (entry `sde_bead_kernel`): one CTA of `block` threads per trajectory, at most

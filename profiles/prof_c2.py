@@ -14,6 +14,8 @@ if os.environ.get("BLOCK"):
     solver.block_size = int(os.environ["BLOCK"])
 if os.environ.get("MINB"):
     solver.min_blocks_per_sm = int(os.environ["MINB"])
+if os.environ.get("WS"):
+    solver.warp_specialize = bool(int(os.environ["WS"]))
 if os.environ.get("LOCKSTEP"):
     solver.lockstep = bool(int(os.environ["LOCKSTEP"]))
 obs = workloads.polar_error_observables(4.0, 2.0)

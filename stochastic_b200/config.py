@@ -8,6 +8,9 @@ _STATE = {
     # "original": threefry counter layout of jax < 0.5 (jax_threefry_partitionable=False; the layout the
     # reference's shipped golden trajectories were generated with); "partitionable": jax >= 0.5 default.
     "prng_layout": "original",
+    # Wagner-Platen with several noise terms: use the producer/consumer kernel (csrc/sde_kernel_ws.cuh) whenever
+    # its two-stage ring of staged normals fits in shared memory.  False forces the single-role kernel.
+    "warp_specialize": True,
 }
 
 

@@ -343,7 +343,10 @@ struct StepScale {
 #define SDE_STEP_BLOCK 1
 #endif
 // element k of this thread's staging column (stage points at the thread's slot of row 0)
-#define SDE_STAGE(k) stage[(k) * SDE_BLOCK]
+#ifndef SDE_STAGE_STRIDE
+#define SDE_STAGE_STRIDE SDE_BLOCK   // threads sharing one staging row
+#endif
+#define SDE_STAGE(k) stage[(k) * SDE_STAGE_STRIDE]
 
 // compile-time helpers ---------------------------------------------------------------------
 #if SDE_P <= 16
@@ -559,8 +562,29 @@ struct WienerGen {
     // which turns every term of the C and D double sums into a single FMA, and shares the
     // correlation / convolution partial sums between D[j1,.,j3] and D[j3,.,j1].
     __device__ __forceinline__ void gen_wagner_platen(u32 s, const StepScale& sc, Integrals& I, real* stage) const {
+        wp_draw(s, stage);
+        wp_assemble(sc, I, stage);
+    }
+
+    // (key, element, size) of staged normal n of step s: n < MP zeta, < 2MP eta, then xi, mu, phi (M each)
+    __device__ __forceinline__ void wp_item(u32 s, int n, Key& key, u32& e, u32& size) const {
         constexpr int M = SDE_M, P = SDE_P;
-        // -- normals: rolled loops into the staging column -------------------------------------
+        if (n < 2 * P * M) {
+            const bool first = n < P * M;
+            key = first ? k_zeta : k_eta;
+            e = s * (u32)(P * M) + (u32)(first ? n : n - P * M);
+            size = S * (u32)(P * M);
+        } else {
+            const int q = n - 2 * P * M;
+            key = (q < M) ? k_xi : ((q < 2 * M) ? k_mu : k_phi);
+            e = s * M + (u32)(q % M);
+            size = S * M;
+        }
+    }
+
+    // -- normals of step s: rolled loops into the staging column
+    __device__ __forceinline__ void wp_draw(u32 s, real* stage) const {
+        constexpr int M = SDE_M, P = SDE_P;
         // 2M independent normals per iteration: enough instruction-level parallelism to cover the
         // dependent threefry rounds / Horner chains with only two resident warps per scheduler.
         {
@@ -599,6 +623,11 @@ struct WienerGen {
                 SDE_STAGE(2 * P * M + 2 * M + j) = nn[2];
             }
         }
+    }
+
+    // -- staged normals -> iterated integrals of one step
+    __device__ __forceinline__ void wp_assemble(const StepScale& sc, Integrals& I, const real* stage) const {
+        constexpr int M = SDE_M, P = SDE_P;
         real xi[M], a[M], b[M];
         real zs[M][P + 1], es[M][P + 1];
         {

@@ -1,0 +1,229 @@
+// sde_kernel_ws.cuh - warp-specialised variant of the stepping kernel for schemes whose per-step random
+// input is large (Wagner-Platen with m > 1: 2mp + 3m normals per step).
+//
+// Same entry point, arguments and results as sde_kernel.cuh.  The CTA is split into
+//   * one CONSUMER warpgroup (128 threads = 128 trajectories): keeps (t, x, w) in registers, turns the staged
+//     normals of a step into iterated integrals (WienerGen::wp_assemble) and applies the emitted sde_step;
+//   * two PRODUCER warpgroups (256 threads): nothing but threefry2x32 + erf_inv, writing the normals of the
+//     next step into a two-stage shared-memory ring.
+// The roles need very different register files, so the producers shrink theirs and the consumers grow theirs
+// with `setmaxnreg` (Hopper/Blackwell register re-allocation between warpgroups); the hand-off uses named
+// barriers (full[stage]: producers arrive, consumers wait; empty[stage]: the reverse).  The integer-heavy RNG
+// and the FP64-heavy integrals then overlap on every scheduler by construction instead of by the accident of
+// two CTAs drifting out of phase, and the tight producer loop keeps issuing while the consumers' long
+// straight-line code waits on instruction fetch.
+//
+// Included AFTER sde_core.cuh (with SDE_STAGE_STRIDE = 128 defined before it) and the problem's device functions.
+#pragma once
+
+#ifndef SDE_NOBS
+#define SDE_NOBS 0
+#endif
+#ifndef SDE_HAS_POST
+#define SDE_HAS_POST 0
+#endif
+#ifndef SDE_WS_CONSUMER_REGS
+#define SDE_WS_CONSUMER_REGS 160
+#endif
+#ifndef SDE_WS_PRODUCER_REGS
+#define SDE_WS_PRODUCER_REGS 40
+#endif
+#ifndef SDE_WS_GROUP
+#define SDE_WS_GROUP 2                // normals a producer thread generates together
+#endif
+#ifndef SDE_WS_PGROUPS
+#define SDE_WS_PGROUPS 2              // producer warpgroups per consumer warpgroup
+#endif
+#define SDE_WS_NC 128                 // consumer threads = trajectories per CTA
+#define SDE_WS_NP (128 * SDE_WS_PGROUPS)   // producer threads
+static_assert(SDE_BLOCK == SDE_WS_NC + SDE_WS_NP, "SDE_BLOCK must be 128 consumers + 128 per producer warpgroup");
+static_assert(SDE_STAGE_STRIDE == SDE_WS_NC, "staging rows hold one value per consumer");
+static_assert(SDE_STAGE_COUNT > 0, "warp specialisation is for staged generators");
+
+namespace sdeb {
+
+struct SolveArgs {   // identical to sde_kernel.cuh
+    u32 key_a, key_b;
+    u32 n_fragments, cpr, chunk, n_snapshots;
+    u64 n_traj_total, traj_begin, traj_count;
+    const real* x0;
+    long long x0_stride;
+    double dt, dt32;
+    real* out_t;
+    real* out_x;
+    real* out_w;
+    double* moments;
+};
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+}  // namespace sdeb
+
+extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(const sdeb::SolveArgs A) {
+    using namespace sdeb;
+    constexpr int NC = SDE_WS_NC, NP = SDE_WS_NP, ALL = SDE_BLOCK;
+    constexpr int FULL0 = 1, EMPTY0 = 3, CONS = 5;            // named barrier ids (0 is __syncthreads)
+    real* const ring = reinterpret_cast<real*>(sde_dyn_smem);  // [2][SDE_STAGE_COUNT][NC]
+    const bool is_consumer = threadIdx.x < NC;
+    const int c = threadIdx.x & (NC - 1);                      // trajectory slot served by this thread
+    const u64 tid_raw = (u64)blockIdx.x * NC + c;
+    const bool active = tid_raw < A.traj_count;
+    const u64 tid = active ? tid_raw : 0;                      // slots past the end redo trajectory 0, no stores
+    const u32 S = A.chunk * A.cpr;
+    // total steps of this launch: whole chunks only, at most n_snapshots of them
+    const u64 total_steps = (u64)A.n_snapshots * A.chunk;
+
+    Key root;
+    root.a = A.key_a;
+    root.b = A.key_b;
+    const Key tkey = split_key(root, A.n_traj_total, A.traj_begin + tid);
+
+    if (!is_consumer) {
+        // ================================ producers =====================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SDE_WS_PRODUCER_REGS));
+        constexpr int PG = SDE_WS_PGROUPS;
+        const int half = (threadIdx.x - NC) >> 7;              // producer warpgroup pg serves slots n = pg (mod PG)
+        WienerGen gen;
+        u32 frag = 0xffffffffu;
+        for (u64 g = 0; g < total_steps; ++g) {
+            const u32 f = (u32)(g / S), s = (u32)(g % S);
+            if (f != frag) {
+                frag = f;
+                gen.init(split_key(tkey, A.n_fragments, f), S);
+            }
+            const int st = (int)(g & 1);
+            if (g >= 2) bar_sync(EMPTY0 + st, ALL);            // consumers have drained this stage
+            real* const col = ring + (size_t)st * SDE_STAGE_COUNT * NC + c;
+            // this thread's slots: n = half, half + PG, ... ; SDE_WS_GROUP of them per iteration (independent chains)
+            constexpr int G = SDE_WS_GROUP;
+            constexpr int SERIES = 2 * SDE_P * SDE_M;             // zeta then eta, SDE_P * SDE_M each
+            const u32 base = s * (u32)(SDE_P * SDE_M), size = S * (u32)(SDE_P * SDE_M);
+#pragma unroll 1
+            for (int n = half; n < SERIES; n += PG * G) {
+                Key kk[G];
+                u32 ee[G], ss[G];
+                real nn[G];
+                int slot[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int ni = (n + PG * i < SERIES) ? n + PG * i : n;    // past the end: repeat (rare)
+                    const bool first = ni < SDE_P * SDE_M;
+                    slot[i] = ni;
+                    kk[i] = first ? gen.k_zeta : gen.k_eta;
+                    ee[i] = base + (u32)(first ? ni : ni - SDE_P * SDE_M);
+                    ss[i] = size;
+                }
+                normal_group<G>(kk, ee, ss, nn);
+#pragma unroll
+                for (int i = 0; i < G; ++i) col[slot[i] * NC] = nn[i];
+            }
+            {   // xi, mu, phi: 3 SDE_M slots, this thread takes those with its parity
+                constexpr int T = (3 * SDE_M + PG - 1) / PG;
+                Key kk[T];
+                u32 ee[T], ss[T];
+                real nn[T];
+                int slot[T];
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    int q = half + PG * i;
+                    if (q >= 3 * SDE_M) q = half;
+                    slot[i] = SERIES + q;
+                    kk[i] = (q < SDE_M) ? gen.k_xi : ((q < 2 * SDE_M) ? gen.k_mu : gen.k_phi);
+                    ee[i] = s * SDE_M + (u32)(q % SDE_M);
+                    ss[i] = S * SDE_M;
+                }
+                normal_group<T>(kk, ee, ss, nn);
+#pragma unroll
+                for (int i = 0; i < T; ++i) col[slot[i] * NC] = nn[i];
+            }
+            __threadfence_block();
+            bar_arrive(FULL0 + st, ALL);
+        }
+        return;
+    }
+
+    // ==================================== consumers =====================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(SDE_WS_CONSUMER_REGS));
+#if SDE_NOBS > 0
+    double obs[SDE_NOBS];
+#pragma unroll
+    for (int k = 0; k < SDE_NOBS; ++k) obs[k] = 0.0;
+#endif
+    {
+        real x[SDE_D], w[SDE_M];
+        real t = RC(0.0);
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) x[i] = A.x0[tid * (u64)A.x0_stride + i];
+#pragma unroll
+        for (int j = 0; j < SDE_M; ++j) w[j] = RC(0.0);
+        StepScale sc;
+        sc.dt = (real)A.dt;
+        sc.sqrt_dt = sqrt((real)A.dt);
+        sc.dt32 = (real)A.dt32;
+        WienerGen gen;                                         // only S is used on this side
+        gen.S = S;
+        u32 snap = 0, in_chunk = 0;
+        for (u64 g = 0; g < total_steps; ++g) {
+            const int st = (int)(g & 1);
+            bar_sync(FULL0 + st, ALL);                         // normals of step g are in the ring
+            Integrals I;
+            gen.wp_assemble(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c);
+            // the staged values were copied to registers at the top of wp_assemble; the integrals depend on all
+            // of them, so by now the stage may be refilled (only if a producer will wait for it)
+            if (g + 2 < total_steps) bar_arrive(EMPTY0 + st, ALL);
+            t += sc.dt;
+            sde_step(x, I, sc.dt);
+#if SDE_HAS_POST
+            sde_post(x);
+#endif
+#pragma unroll
+            for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
+            if (++in_chunk < A.chunk) continue;
+            in_chunk = 0;
+            if (active) {
+                const u64 row = tid * (u64)A.n_snapshots + snap;
+                if (A.out_t) A.out_t[row] = t;
+                if (A.out_x) {
+#pragma unroll
+                    for (int i = 0; i < SDE_D; ++i) A.out_x[row * SDE_D + i] = x[i];
+                }
+                if (A.out_w) {
+#pragma unroll
+                    for (int j = 0; j < SDE_M; ++j) A.out_w[row * SDE_M + j] = w[j];
+                }
+            }
+            ++snap;
+        }
+#if SDE_NOBS > 0
+        sde_observe(x, w, t, obs);
+#endif
+    }
+#if SDE_NOBS > 0
+    __shared__ double red[2 * SDE_NOBS][SDE_WS_NC / 32];
+    const int red_lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < SDE_NOBS; ++k) {
+        double s1 = active ? obs[k] : 0.0;
+        double s2 = s1 * s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if (red_lane == 0) {
+            red[2 * k][wid] = s1;
+            red[2 * k + 1][wid] = s2;
+        }
+    }
+    bar_sync(CONS, NC);
+    if (threadIdx.x < 2 * SDE_NOBS && A.moments) {
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < SDE_WS_NC / 32; ++v) s += red[threadIdx.x][v];
+        atomicAdd(&A.moments[threadIdx.x], s);
+    }
+#endif
+}

@@ -201,8 +201,8 @@ int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, in
     return 0;
 }
 
-int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, size_t dyn_smem_bytes,
-                  void* stream) {
+int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, int traj_per_block,
+                  size_t dyn_smem_bytes, void* stream) {
     if (!prog || !args) return fail(-1, "sdeb200_solve: null argument");
     if (block <= 0 || block > 1024 || (block % 32)) return fail(-1, "sdeb200_solve: bad block size");
     if (args->traj_count == 0) return 0;
@@ -214,7 +214,9 @@ int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int
     if ((uint64_t)args->n_snapshots > (uint64_t)args->n_fragments * args->cpr)
         return fail(-1, "sdeb200_solve: n_snapshots exceeds n_fragments * cpr");
     if (!(args->dt > 0)) return fail(-1, "sdeb200_solve: dt must be positive");
-    uint64_t grid = (args->traj_count + (uint64_t)block - 1) / (uint64_t)block;
+    if (traj_per_block < 0 || traj_per_block > block) return fail(-1, "sdeb200_solve: bad traj_per_block");
+    const uint64_t per = traj_per_block ? (uint64_t)traj_per_block : (uint64_t)block;
+    uint64_t grid = (args->traj_count + per - 1) / per;
     if (grid > 0x7fffffffULL) return fail(-1, "sdeb200_solve: too many trajectories for one launch");
     if (int e = ensure_smem(prog, dyn_smem_bytes)) return e;
     sdeb200_solve_args_t a = *args;

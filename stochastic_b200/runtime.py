@@ -94,8 +94,8 @@ def lib():
         L.sdeb200_program_destroy.argtypes = [ctypes.c_void_p]
         L.sdeb200_program_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
-        L.sdeb200_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(SolveArgs), ctypes.c_int, ctypes.c_size_t,
-                                    ctypes.c_void_p]
+        L.sdeb200_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(SolveArgs), ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_size_t, ctypes.c_void_p]
         L.sdeb200_wiener_integrals.argtypes = [ctypes.c_void_p, ctypes.POINTER(WienerArgs), ctypes.c_int,
                                                ctypes.c_size_t, ctypes.c_void_p]
         L.sdeb200_bead_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(BeadArgs), ctypes.c_int, ctypes.c_size_t,
@@ -174,7 +174,7 @@ def current_stream_ptr():
 # ------------------------------------------------------------------------------------------
 def _core_fingerprint():
     h = hashlib.sha256()
-    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_wiener_kernel.cuh", "sde_bead_kernel.cuh"):
+    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh", "sde_bead_kernel.cuh"):
         with open(os.path.join(CSRC_DIR, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()

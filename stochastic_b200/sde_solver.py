@@ -95,17 +95,84 @@ def _c_function(name, signature, outputs, var_names, f64):
     return f"__device__ __forceinline__ void {name}({signature}) {{\n{body}\n}}\n"
 
 
+def _emit_post(post, d, f64):
+    x = jnp.symbols((d,))
+    y = np.asarray(jnp._as_obj(post(x)), dtype=object)
+    if y.shape != (d,):
+        raise ValueError(f"step_post_processing returned shape {y.shape}, expected {(d,)}")
+    names = {i: f"x[{i}]" for i in range(d)}
+    return _c_function("sde_post", "real (&x)[SDE_D]", [(f"x[{i}]", E.wrap(v)) for i, v in enumerate(y)], names, f64), d
+
+
+def _emit_observe(observe, d, m, f64):
+    x = jnp.symbols((d,))
+    w = jnp.symbols((m,), start=d)
+    t = E.var(d + m)
+    o = np.atleast_1d(np.asarray(jnp._as_obj(observe(x, w, t)), dtype=object)).ravel()
+    names = {i: f"x[{i}]" for i in range(d)}
+    names.update({d + j: f"w[{j}]" for j in range(m)})
+    names[d + m] = "t"
+    src = _c_function("sde_observe", "const real* x, const real* w, const real t, double (&obs)[SDE_NOBS]",
+                      [(f"obs[{k}]", E.wrap(v)) for k, v in enumerate(o)], names, f64)
+    return src, o.size
+
+
 def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observe=None, p=10, block=None,
-                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None):
+                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None):
     """Trace the problem and emit the complete translation unit of its stepping kernel.
 
-    Returns (source, m, n_obs, block, dyn_smem_bytes)."""
+    Returns (source, m, n_obs, block, dyn_smem_bytes); `build_source.traj_per_block` of the last call is the number
+    of trajectories per CTA (128 for the warp-specialised kernel, else block)."""
     E.trim_table()
     tp = TracedProblem(problem_a, problem_b, d)
     m = tp.m
     outs, sv = step_expressions(tp, scheme)
-    block = runtime.pick_block(m, p, scheme, f64, block)
     stage = runtime.stage_count(m, p, scheme)
+    elem = 8 if f64 else 4
+    if warp_specialize is None:
+        warp_specialize = config.get("warp_specialize")
+    ws = bool(warp_specialize) and scheme == "wagner_platen" and m > 1 and 2 * stage * 128 * elem <= 110 * 1024
+    if ws:
+        # warp-specialised kernel (csrc/sde_kernel_ws.cuh): 128 consumer + 256 producer threads, two-stage ring
+        parts = [
+            "// generated by stochastic_b200.sde_solver.build_source (warp-specialised)",
+            f"#define SDE_D {d}", f"#define SDE_M {m}", f"#define SDE_SCHEME {SCHEME_ID[scheme]}",
+            f"#define SDE_P {int(p)}", f"#define SDE_F64 {1 if f64 else 0}",
+            f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}",
+            "#define SDE_STAGE_STRIDE 128",
+        ]
+        import os as _os   # tuning knobs of the warp-specialised kernel (profiles/README.md)
+        # measured on B200 (profiles/README.md): 3 producer warpgroups per consumer warpgroup, one normal at a time
+        knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1}
+        for knob in list(knobs):
+            if _os.environ.get(knob):
+                knobs[knob] = int(_os.environ[knob])
+        ws_block = 128 * (1 + knobs["SDE_WS_PGROUPS"])
+        launch_regs = (65536 // (2 * ws_block)) // 8 * 8            # __launch_bounds__(ws_block, 2)
+        need = 128 * knobs["SDE_WS_CONSUMER_REGS"] + 128 * knobs["SDE_WS_PGROUPS"] * knobs["SDE_WS_PRODUCER_REGS"]
+        if need > launch_regs * ws_block or knobs["SDE_WS_CONSUMER_REGS"] % 8 or knobs["SDE_WS_PRODUCER_REGS"] % 8:
+            raise ValueError(f"warp-specialised register split {knobs} exceeds the CTA's {launch_regs * ws_block} "
+                             "registers (setmaxnreg.inc would never be granted)")
+        parts.append(f"#define SDE_BLOCK {ws_block}")
+        for knob, val in knobs.items():
+            parts.append(f"#define {knob} {val}")
+        n_obs = 0
+        post_src = obs_src = ""
+        if post is not None:
+            post_src, _ = _emit_post(post, d, f64)
+            parts.append("#define SDE_HAS_POST 1")
+        if observe is not None:
+            obs_src, n_obs = _emit_observe(observe, d, m, f64)
+            parts.append(f"#define SDE_NOBS {n_obs}")
+        parts.append('#include "sde_core.cuh"')
+        parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
+        parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
+                                 [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
+        parts += [post_src, obs_src, '#include "sde_kernel_ws.cuh"']
+        build_source.traj_per_block = 128
+        return "\n".join(parts) + "\n", m, n_obs, ws_block, 2 * stage * 128 * elem
+    block = runtime.pick_block(m, p, scheme, f64, block)
+    build_source.traj_per_block = block
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
         min_blocks = 2
@@ -115,7 +182,7 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         f"#define SDE_P {int(p)}", f"#define SDE_F64 {1 if f64 else 0}",
         f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {int(block)}",
     ]
-    stage_bytes = stage * block * (8 if f64 else 4)
+    stage_bytes = stage * block * elem
     if snap_tile is None:
         snap_tile = runtime.pick_snap_tile(d, m, block, f64, stage_bytes, n_snapshots)
     if snap_tile > 1:
@@ -127,25 +194,10 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     n_obs = 0
     post_src = obs_src = ""
     if post is not None:
-        x = jnp.symbols((d,))
-        y = np.asarray(jnp._as_obj(post(x)), dtype=object)
-        if y.shape != (d,):
-            raise ValueError(f"step_post_processing returned shape {y.shape}, expected {(d,)}")
-        names = {i: f"x[{i}]" for i in range(d)}
-        post_src = _c_function("sde_post", "real (&x)[SDE_D]", [(f"x[{i}]", E.wrap(v)) for i, v in enumerate(y)],
-                               names, f64)
+        post_src, _ = _emit_post(post, d, f64)
         parts.append("#define SDE_HAS_POST 1")
     if observe is not None:
-        x = jnp.symbols((d,))
-        w = jnp.symbols((m,), start=d)
-        t = E.var(d + m)
-        o = np.atleast_1d(np.asarray(jnp._as_obj(observe(x, w, t)), dtype=object)).ravel()
-        n_obs = o.size
-        names = {i: f"x[{i}]" for i in range(d)}
-        names.update({d + j: f"w[{j}]" for j in range(m)})
-        names[d + m] = "t"
-        obs_src = _c_function("sde_observe", "const real* x, const real* w, const real t, double (&obs)[SDE_NOBS]",
-                              [(f"obs[{k}]", E.wrap(v)) for k, v in enumerate(o)], names, f64)
+        obs_src, n_obs = _emit_observe(observe, d, m, f64)
         parts.append(f"#define SDE_NOBS {n_obs}")
     parts.append('#include "sde_core.cuh"')
     parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
@@ -183,6 +235,7 @@ class SDESolver:
         self.min_blocks_per_sm = None
         self.lockstep = None
         self.snap_tile = None
+        self.warp_specialize = None    # True: producer/consumer kernel for Wagner-Platen with m > 1 (sde_kernel_ws.cuh)
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
 
     def compile(self, problem, step_post_processing=None, observables=None, prng_layout=None):
@@ -193,7 +246,7 @@ class SDESolver:
         layout = prng_layout or config.get("prng_layout")
         source = build_source(problem.a, problem.b, d, self.scheme, f64, layout, post=step_post_processing,
                               observe=observables, block=self.block_size, min_blocks=self.min_blocks_per_sm,
-                              lockstep=self.lockstep)[0]
+                              lockstep=self.lockstep, warp_specialize=self.warp_specialize)[0]
         return runtime.compile_source(source)[0]
 
     # -- the hot path ------------------------------------------------------------------------
@@ -246,7 +299,9 @@ class SDESolver:
                                                          block=self.block_size, min_blocks=self.min_blocks_per_sm,
                                                          lockstep=self.lockstep,
                                                          n_snapshots=(n_snap if store_trajectories else 1),
-                                                         snap_tile=self.snap_tile)
+                                                         snap_tile=self.snap_tile,
+                                                         warp_specialize=self.warp_specialize)
+        traj_per_block = build_source.traj_per_block
         prog = runtime.load_program(source, "sde_solve_kernel")   # raises without a CUDA device
         torch = runtime.require_cuda()
 
@@ -284,7 +339,7 @@ class SDESolver:
             out_w=out_w.data_ptr() if out_w is not None else None,
             moments=moments.data_ptr() if moments is not None else None)
         if count > 0:
-            runtime.check(runtime.lib().sdeb200_solve(prog.handle, ctypes.byref(args), block, dyn_smem,
+            runtime.check(runtime.lib().sdeb200_solve(prog.handle, ctypes.byref(args), block, traj_per_block, dyn_smem,
                                                       runtime.current_stream_ptr()), "sdeb200_solve")
             runtime.STATS["launches"] += 1
         self.last_program = prog

@@ -55,7 +55,7 @@ def test_nvrtc_error_is_reported():
 
 def test_invalid_arguments_are_rejected():
     lib = runtime.lib()
-    assert lib.sdeb200_solve(None, None, 128, 0, None) < 0
+    assert lib.sdeb200_solve(None, None, 128, 0, 0, None) < 0
     assert b"null" in lib.sdeb200_last_error()
     assert lib.sdeb200_wiener_integrals(None, None, 128, 0, None) < 0
     assert lib.sdeb200_keys_split(0, 0, 10, 8, 4, 0, None, None) < 0          # out NULL
