@@ -563,7 +563,7 @@ struct WienerGen {
     // correlation / convolution partial sums between D[j1,.,j3] and D[j3,.,j1].
     __device__ __forceinline__ void gen_wagner_platen(u32 s, const StepScale& sc, Integrals& I, real* stage) const {
         wp_draw(s, stage);
-        wp_assemble(sc, I, stage);
+        wp_assemble(sc, I, stage, [] {});
     }
 
     // (key, element, size) of staged normal n of step s: n < MP zeta, < 2MP eta, then xi, mu, phi (M each)
@@ -625,8 +625,11 @@ struct WienerGen {
         }
     }
 
-    // -- staged normals -> iterated integrals of one step
-    __device__ __forceinline__ void wp_assemble(const StepScale& sc, Integrals& I, const real* stage) const {
+    // -- staged normals -> iterated integrals of one step; `after_reads()` is invoked once every staged value
+    //    has been copied into registers (the warp-specialised kernel releases the ring stage there)
+    template <class AfterReads>
+    __device__ __forceinline__ void wp_assemble(const StepScale& sc, Integrals& I, const real* stage,
+                                                AfterReads after_reads) const {
         constexpr int M = SDE_M, P = SDE_P;
         real xi[M], a[M], b[M];
         real zs[M][P + 1], es[M][P + 1];
@@ -665,6 +668,7 @@ struct WienerGen {
                 a[j] = -(real)(1.4142135623730950488 / SDE_PI) * sa[j] - two_sqrt_rho * mu;   // sqrt(2)/pi
                 b[j] = fma((real)(1.0 / (1.4142135623730950488 * SDE_PI)), sb[j], sqrt_alpha * phi);  // 1/(sqrt(2) pi)
             }
+            after_reads();
         }
 
         // A (antisymmetric), B (symmetric)

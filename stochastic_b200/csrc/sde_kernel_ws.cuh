@@ -170,10 +170,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             const int st = (int)(g & 1);
             bar_sync(FULL0 + st, ALL);                         // normals of step g are in the ring
             Integrals I;
-            gen.wp_assemble(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c);
-            // the staged values were copied to registers at the top of wp_assemble; the integrals depend on all
-            // of them, so by now the stage may be refilled (only if a producer will wait for it)
-            if (g + 2 < total_steps) bar_arrive(EMPTY0 + st, ALL);
+            // the stage is released as soon as its values sit in registers (only if a producer will wait for it)
+            const bool release = g + 2 < total_steps;
+            gen.wp_assemble(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c, [&] {
+                if (release) bar_arrive(EMPTY0 + st, ALL);
+            });
             t += sc.dt;
             sde_step(x, I, sc.dt);
 #if SDE_HAS_POST
