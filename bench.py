@@ -37,10 +37,11 @@ N_TRAJ_PER_GPU = 10 ** 7
 TMAX = 1.0
 Y_DRIFT = 4.0
 FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10): the contract (algorithmic) figure
-# ncu counters of the dominant launch (10^7 trajectories x 512 steps), profiles/r1_ncu_c2_bench_kernel_counters.csv:
-# DFMA 3703, DMUL 664, DADD 364 thread-instructions per trajectory-step; DRAM 42 MB read + 1961 MB written per launch
+# ncu counters of the warp-specialised kernel (profiles/r1_ncu_c2_ws_counters_2M_x128.csv): DFMA 3703, DMUL 664, DADD 364
+# thread-instructions per trajectory-step; DRAM traffic of the dominant launch, 10^7 trajectories x 512 steps
+# (profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv): 42 MB read + 447 MB written (algorithmic: 400 MB of final states)
 EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3703 + 664 + 364
-DRAM_BYTES_PER_DOMINANT_LAUNCH = 41932288 + 1960619776
+DRAM_BYTES_PER_DOMINANT_LAUNCH = 42117632 + 446696448
 THEORETICAL_MEAN_PHI = 1.10714532096375
 
 
@@ -301,7 +302,7 @@ def run_b200(args):
                              "frac": achieved / fp64_peak,
                              "traffic": DRAM_BYTES_PER_DOMINANT_LAUNCH if n_local == N_TRAJ_PER_GPU else None,
                              "traffic_note": "dram__bytes_read+write of this launch from ncu (round-1 capture, "
-                                             "profiles/r1_ncu_c2_bench_kernel_counters.csv); algorithmic bytes are the "
+                                             "profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv); algorithmic bytes are the "
                                              "400 MB of final states - the kernel is FP64/issue-bound, not HBM-bound",
                              "executed_tflops": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12,
                              "executed_frac": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12 / fp64_peak,
