@@ -118,7 +118,7 @@ def _emit_observe(observe, d, m, f64):
 
 
 def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observe=None, p=10, block=None,
-                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None):
+                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None, ws_tuning=None):
     """Trace the problem and emit the complete translation unit of its stepping kernel.
 
     Returns (source, m, n_obs, block, dyn_smem_bytes); `build_source.traj_per_block` of the last call is the number
@@ -141,12 +141,12 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
             f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}",
             "#define SDE_STAGE_STRIDE 128",
         ]
-        import os as _os   # tuning knobs of the warp-specialised kernel (profiles/README.md)
         # measured on B200 (profiles/README.md): 3 producer warpgroups per consumer warpgroup, one normal at a time
         knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1}
-        for knob in list(knobs):
-            if _os.environ.get(knob):
-                knobs[knob] = int(_os.environ[knob])
+        for knob, val in (ws_tuning or {}).items():
+            if knob not in knobs:
+                raise KeyError(f"unknown warp-specialisation knob {knob!r}")
+            knobs[knob] = int(val)
         ws_block = 128 * (1 + knobs["SDE_WS_PGROUPS"])
         launch_regs = (65536 // (2 * ws_block)) // 8 * 8            # __launch_bounds__(ws_block, 2)
         need = 128 * knobs["SDE_WS_CONSUMER_REGS"] + 128 * knobs["SDE_WS_PGROUPS"] * knobs["SDE_WS_PRODUCER_REGS"]
@@ -235,7 +235,8 @@ class SDESolver:
         self.min_blocks_per_sm = None
         self.lockstep = None
         self.snap_tile = None
-        self.warp_specialize = None    # True: producer/consumer kernel for Wagner-Platen with m > 1 (sde_kernel_ws.cuh)
+        self.warp_specialize = None    # None: config "warp_specialize"; producer/consumer kernel (sde_kernel_ws.cuh)
+        self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
 
     def compile(self, problem, step_post_processing=None, observables=None, prng_layout=None):
@@ -246,7 +247,8 @@ class SDESolver:
         layout = prng_layout or config.get("prng_layout")
         source = build_source(problem.a, problem.b, d, self.scheme, f64, layout, post=step_post_processing,
                               observe=observables, block=self.block_size, min_blocks=self.min_blocks_per_sm,
-                              lockstep=self.lockstep, warp_specialize=self.warp_specialize)[0]
+                              lockstep=self.lockstep, warp_specialize=self.warp_specialize,
+                              ws_tuning=self.ws_tuning)[0]
         return runtime.compile_source(source)[0]
 
     # -- the hot path ------------------------------------------------------------------------
@@ -300,7 +302,8 @@ class SDESolver:
                                                          lockstep=self.lockstep,
                                                          n_snapshots=(n_snap if store_trajectories else 1),
                                                          snap_tile=self.snap_tile,
-                                                         warp_specialize=self.warp_specialize)
+                                                         warp_specialize=self.warp_specialize,
+                                                         ws_tuning=self.ws_tuning)
         traj_per_block = build_source.traj_per_block
         prog = runtime.load_program(source, "sde_solve_kernel")   # raises without a CUDA device
         torch = runtime.require_cuda()

@@ -316,3 +316,21 @@ def test_host_prng_matches_oracle():
                                                                  jax_prng.split(jax_prng.PRNGKey(seed), n, layout)]
     from stochastic_b200.sde_solver import prng_key
     assert prng_key(5) == (0, 5) and prng_key((3, 4)) == (3, 4) and prng_key(1 << 33) == (2, 0)
+
+
+def test_warp_specialised_source_selection_and_register_budget():
+    prob = workloads.polar_walk(4.0, (2.0, 0.0), f64=True)
+    src, m, n_obs, block, smem = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original")
+    assert "sde_kernel_ws.cuh" in src and block == 512 and smem == 2 * 46 * 128 * 8 and build_source.traj_per_block == 128
+    src, _, _, block, _ = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original", warp_specialize=False)
+    assert "sde_kernel_ws.cuh" not in src and block == 256 and build_source.traj_per_block == 256
+    src, _, _, block, _ = build_source(prob.a, prob.b, 2, "milstein", True, "original")
+    assert "sde_kernel_ws.cuh" not in src            # only Wagner-Platen with m > 1 stages its normals
+    prob3, _ = P.coupled_3x3()
+    src = build_source(prob3.a, prob3.b, 3, "wagner_platen", True, "original")[0]
+    assert "sde_kernel_ws.cuh" not in src            # ring of 2 x 69 x 128 doubles does not fit twice per SM
+    with pytest.raises(ValueError):                    # 128*120 + 384*48 registers > 512*64: setmaxnreg would hang
+        build_source(prob.a, prob.b, 2, "wagner_platen", True, "original",
+                     ws_tuning={"SDE_WS_CONSUMER_REGS": 120, "SDE_WS_PRODUCER_REGS": 48})
+    with pytest.raises(KeyError):
+        build_source(prob.a, prob.b, 2, "wagner_platen", True, "original", ws_tuning={"NOPE": 1})
