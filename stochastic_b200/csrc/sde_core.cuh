@@ -231,15 +231,15 @@ static __device__ __noinline__ double erfinv_tail(double x, double w) {
 __device__ __forceinline__ double uniform_pm1(u64 bits) {
     const double lo = -0.99999999999999988898;  // nextafter(-1, 0)
     double f = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)) - 1.0;
-    double u = f * (1.0 - lo) + lo;
-    return fmax(lo, u);
+    // jax clamps with max(lo, .) against rounding below lo; here hi - lo rounds to exactly 2, f * 2 is exact and
+    // f >= 0, so f * 2 + lo >= lo already holds after rounding and the clamp is the identity
+    return fma(f, 2.0, lo);
 }
 
 __device__ __forceinline__ float uniform_pm1(u32 bits) {
     const float lo = -0.99999994f;  // nextafter(-1f, 0f)
     float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
-    float u = f * (1.0f - lo) + lo;
-    return fmaxf(lo, u);
+    return fmaf(f, 2.0f, lo);   // the clamp max(lo, .) is the identity here, see the double version
 }
 
 // N standard normals at once: out[i] = element e[i] of jax.random.normal(key[i], shape with size[i]
