@@ -176,6 +176,13 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
         min_blocks = 2
+    if min_blocks is None and not stage and block == 128:
+        # small step functions: cap the kernel at 80 registers so that six CTAs are resident per SM - the normal
+        # generator is latency-bound and gains more from extra warps than from registers (two spheres +20 %, polar
+        # Euler +55 %, GARCH Milstein +10 %; the 1 640-node four-bead step function loses 20 % and is left alone)
+        n_nodes = sum(1 for node in E.topo_order(outs) if node.op not in ("const", "var"))
+        if n_nodes <= 800:
+            min_blocks = 6
     parts = [
         "// generated by stochastic_b200.sde_solver.build_source",
         f"#define SDE_D {d}", f"#define SDE_M {m}", f"#define SDE_SCHEME {SCHEME_ID[scheme]}",
