@@ -1,0 +1,39 @@
+"""The reference's own benchmark workloads (benchmarks/benchmark_sde_solver.py:12-126: scalar SDE
+dx = -x(1-x^2) dt + (1-x^2) dw, x0 = 0.5, tmax = 5, 100 steps; default float32) through the drop-in API,
+timed the way pytest-benchmark times them: wall clock of solve(...)["solution_values"].block_until_ready(),
+host work (trace, emit, cache lookup, launch) included."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import stochastic_b200 as pychastic
+
+scalar_tanh = pychastic.sde_problem.SDEProblem(
+    a=lambda x: -x * (1 - x ** 2), b=lambda x: 1 - x ** 2, x0=0.5, tmax=5.0,
+    exact_solution=lambda x0, t, w: np.tanh(w + np.arctanh(x0)))
+steps = 100
+cases = [("single_trajectory", "euler", 1), ("2k_trajectories", "euler", 2000), ("2k_trajectories_milstein", "milstein", 2000),
+         ("2k_trajectories_wagner_platen", "wagner_platen", 2000), ("20k_trajectories", "euler", 20000),
+         ("200k_trajectories", "euler", 200000), ("2M_trajectories", "euler", 2000000)]
+rows = []
+for name, scheme, n in cases:
+    solver = pychastic.sde_solver.SDESolver()
+    solver.dt = scalar_tanh.tmax / steps
+    solver.scheme = scheme
+
+    def to_benchmark():
+        if n == 1:
+            return solver.solve(scalar_tanh)["solution_values"].block_until_ready()
+        return solver.solve_many(scalar_tanh, n)["solution_values"].block_until_ready()
+
+    to_benchmark()                      # first call: NVRTC / cubin cache
+    times = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        to_benchmark()
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    rows.append({"benchmark": name, "scheme": scheme, "n_trajectories": n, "median_ms": med * 1e3, "min_ms": min(times) * 1e3,
+                 "traj_steps_per_s": n * steps / med})
+    print(json.dumps(rows[-1]), flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/reference_benchmarks_r1.json", "w"), indent=1)
