@@ -9,6 +9,7 @@
 //   __device__ void sde_step(real (&x)[SDE_D], const sdeb::Integrals& I, real dt);   // required
 //   __device__ void sde_post(real (&x)[SDE_D]);                      // if SDE_HAS_POST
 //   __device__ void sde_observe(const real*, const real*, real, double (&obs)[SDE_NOBS]);  // if SDE_NOBS > 0
+//   __device__ real sde_event(const real* x, const real* w, real t);                      // if SDE_HAS_EVENT
 #pragma once
 
 #ifndef SDE_NOBS
@@ -16,6 +17,9 @@
 #endif
 #ifndef SDE_HAS_POST
 #define SDE_HAS_POST 0
+#endif
+#ifndef SDE_HAS_EVENT
+#define SDE_HAS_EVENT 0   // 1: sde_event(x, w, t) is watched for its first crossing of zero
 #endif
 #ifndef SDE_MIN_BLOCKS
 #define SDE_MIN_BLOCKS 1
@@ -50,6 +54,7 @@ struct SolveArgs {
     real* out_x;              // (traj_count, n_snapshots, SDE_D)     or nullptr
     real* out_w;              // (traj_count, n_snapshots, SDE_M)     or nullptr
     double* moments;          // (SDE_NOBS, 2): sum, sum of squares   or nullptr
+    real* out_hit;            // (traj_count, 2 + SDE_D): flag, time, state of the first passage   or nullptr
 };
 
 }  // namespace sdeb
@@ -98,6 +103,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
         sc.dt = (real)A.dt;
         sc.sqrt_dt = sqrt((real)A.dt);
         sc.dt32 = (real)A.dt32;
+#if SDE_HAS_EVENT
+        // first-passage observer: the first step after which sde_event(x, w, t) > 0, located by linear interpolation
+        // between the states before and after that step (reference examples/hit.py:40-58, done on the device)
+        real ev_prev = sde_event(x, w, t);
+        real hit_t = RC(0.0), hit_x[SDE_D];
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) hit_x[i] = RC(0.0);
+#endif
         const u32 S = A.chunk * A.cpr;
         u32 snap = 0;
         for (u32 f = 0; f < A.n_fragments && snap < A.n_snapshots; ++f) {
@@ -116,6 +130,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
                 for (int b = 0; b < SDE_STEP_BLOCK; ++b) {
                     if (s0 + b >= S || snap >= A.n_snapshots) break;
                     const Integrals& I = Iblk[b];
+#if SDE_HAS_EVENT
+                    real x_before[SDE_D];
+#pragma unroll
+                    for (int i = 0; i < SDE_D; ++i) x_before[i] = x[i];
+#endif
                     t += sc.dt;
                     sde_step(x, I, sc.dt);
 #if SDE_HAS_POST
@@ -123,6 +142,19 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
 #endif
 #pragma unroll
                     for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
+#if SDE_HAS_EVENT
+                    {
+                        const real ev_now = sde_event(x, w, t);
+                        if (!hit && ev_now > RC(0.0)) {
+                            const real wgt = (RC(0.0) - ev_prev) / (ev_now - ev_prev);
+                            hit = true;
+                            hit_t = (t - sc.dt) + wgt * sc.dt;
+#pragma unroll
+                            for (int i = 0; i < SDE_D; ++i) hit_x[i] = x[i] * wgt + x_before[i] * (RC(1.0) - wgt);
+                        }
+                        ev_prev = ev_now;
+                    }
+#endif
                     if (++in_chunk < A.chunk) continue;
                     in_chunk = 0;
                     // ---- snapshot `snap` -----------------------------------------------------------------
@@ -195,6 +227,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
                 }
             }
         }
+#if SDE_HAS_EVENT
+        if (active && A.out_hit) {
+            real* o = A.out_hit + tid * (u64)(2 + SDE_D);
+            o[0] = hit ? RC(1.0) : RC(0.0);
+            o[1] = hit_t;
+#pragma unroll
+            for (int i = 0; i < SDE_D; ++i) o[2 + i] = hit_x[i];
+        }
+#endif
 #if SDE_NOBS > 0
         sde_observe(x, w, t, obs);
 #endif

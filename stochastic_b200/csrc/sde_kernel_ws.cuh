@@ -22,6 +22,9 @@
 #ifndef SDE_HAS_POST
 #define SDE_HAS_POST 0
 #endif
+#ifndef SDE_HAS_EVENT
+#define SDE_HAS_EVENT 0
+#endif
 #ifndef SDE_WS_CONSUMER_REGS
 #define SDE_WS_CONSUMER_REGS 160
 #endif
@@ -53,6 +56,7 @@ struct SolveArgs {   // identical to sde_kernel.cuh
     real* out_x;
     real* out_w;
     double* moments;
+    real* out_hit;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -163,6 +167,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
         sc.dt = (real)A.dt;
         sc.sqrt_dt = sqrt((real)A.dt);
         sc.dt32 = (real)A.dt32;
+#if SDE_HAS_EVENT
+        // first-passage observer: the first step after which sde_event(x, w, t) > 0, located by linear interpolation
+        // between the states before and after that step (reference examples/hit.py:40-58, done on the device)
+        real ev_prev = sde_event(x, w, t);
+        real hit_t = RC(0.0), hit_x[SDE_D];
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) hit_x[i] = RC(0.0);
+#endif
         WienerGen gen;                                         // only S is used on this side
         gen.S = S;
         u32 snap = 0, in_chunk = 0;
@@ -175,6 +188,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             gen.wp_assemble(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c, [&] {
                 if (release) bar_arrive(EMPTY0 + st, ALL);
             });
+#if SDE_HAS_EVENT
+            real x_before[SDE_D];
+#pragma unroll
+            for (int i = 0; i < SDE_D; ++i) x_before[i] = x[i];
+#endif
             t += sc.dt;
             sde_step(x, I, sc.dt);
 #if SDE_HAS_POST
@@ -182,6 +200,19 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 #endif
 #pragma unroll
             for (int j = 0; j < SDE_M; ++j) w[j] += I.dW[j];
+#if SDE_HAS_EVENT
+            {
+                const real ev_now = sde_event(x, w, t);
+                if (!hit && ev_now > RC(0.0)) {
+                    const real wgt = (RC(0.0) - ev_prev) / (ev_now - ev_prev);
+                    hit = true;
+                    hit_t = (t - sc.dt) + wgt * sc.dt;
+#pragma unroll
+                    for (int i = 0; i < SDE_D; ++i) hit_x[i] = x[i] * wgt + x_before[i] * (RC(1.0) - wgt);
+                }
+                ev_prev = ev_now;
+            }
+#endif
             if (++in_chunk < A.chunk) continue;
             in_chunk = 0;
             if (active) {
@@ -198,6 +229,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             }
             ++snap;
         }
+#if SDE_HAS_EVENT
+        if (active && A.out_hit) {
+            real* o = A.out_hit + tid * (u64)(2 + SDE_D);
+            o[0] = hit ? RC(1.0) : RC(0.0);
+            o[1] = hit_t;
+#pragma unroll
+            for (int i = 0; i < SDE_D; ++i) o[2 + i] = hit_x[i];
+        }
+#endif
 #if SDE_NOBS > 0
         sde_observe(x, w, t, obs);
 #endif

@@ -32,7 +32,7 @@ class SolveArgs(ctypes.Structure):
         ("x0", ctypes.c_void_p), ("x0_stride", ctypes.c_int64),
         ("dt", ctypes.c_double), ("dt32", ctypes.c_double),
         ("out_t", ctypes.c_void_p), ("out_x", ctypes.c_void_p), ("out_w", ctypes.c_void_p),
-        ("moments", ctypes.c_void_p),
+        ("moments", ctypes.c_void_p), ("out_hit", ctypes.c_void_p),
     ]
 
 
@@ -60,7 +60,7 @@ class BeadArgs(ctypes.Structure):
     ]
 
 
-assert ctypes.sizeof(SolveArgs) == 112 and ctypes.sizeof(WienerArgs) == 56 and ctypes.sizeof(BeadArgs) == 152
+assert ctypes.sizeof(SolveArgs) == 120 and ctypes.sizeof(WienerArgs) == 56 and ctypes.sizeof(BeadArgs) == 152
 
 _lib = None
 _lib_lock = threading.Lock()

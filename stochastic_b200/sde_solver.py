@@ -117,8 +117,24 @@ def _emit_observe(observe, d, m, f64):
     return src, o.size
 
 
+def _emit_event(event, d, m, f64):
+    x = jnp.symbols((d,))
+    w = jnp.symbols((m,), start=d)
+    t = E.var(d + m)
+    g = np.asarray(jnp._as_obj(event(x, w, t)), dtype=object).ravel()
+    if g.size != 1:
+        raise ValueError(f"first_passage must return one scalar, got {g.size} values")
+    names = {i: f"x[{i}]" for i in range(d)}
+    names.update({d + j: f"w[{j}]" for j in range(m)})
+    names[d + m] = "t"
+    body = emit.emit_body([("ev", E.wrap(g[0]))], names, f64=f64)
+    return ("__device__ __forceinline__ real sde_event(const real* x, const real* w, const real t) {\n"
+            f"    real ev;\n{body}\n    return ev;\n}}\n")
+
+
 def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observe=None, p=10, block=None,
-                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None, ws_tuning=None):
+                 min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None, ws_tuning=None,
+                 event=None):
     """Trace the problem and emit the complete translation unit of its stepping kernel.
 
     Returns (source, m, n_obs, block, dyn_smem_bytes); `build_source.traj_per_block` of the last call is the number
@@ -164,11 +180,15 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         if observe is not None:
             obs_src, n_obs = _emit_observe(observe, d, m, f64)
             parts.append(f"#define SDE_NOBS {n_obs}")
+        ev_src = ""
+        if event is not None:
+            ev_src = _emit_event(event, d, m, f64)
+            parts.append("#define SDE_HAS_EVENT 1")
         parts.append('#include "sde_core.cuh"')
         parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
         parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
                                  [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
-        parts += [post_src, obs_src, '#include "sde_kernel_ws.cuh"']
+        parts += [post_src, obs_src, ev_src, '#include "sde_kernel_ws.cuh"']
         build_source.traj_per_block = 128
         return "\n".join(parts) + "\n", m, n_obs, ws_block, 2 * stage * 128 * elem
     block = runtime.pick_block(m, p, scheme, f64, block)
@@ -206,12 +226,17 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     if observe is not None:
         obs_src, n_obs = _emit_observe(observe, d, m, f64)
         parts.append(f"#define SDE_NOBS {n_obs}")
+    ev_src = ""
+    if event is not None:
+        ev_src = _emit_event(event, d, m, f64)
+        parts.append("#define SDE_HAS_EVENT 1")
     parts.append('#include "sde_core.cuh"')
     parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
     parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
                              [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
     parts.append(post_src)
     parts.append(obs_src)
+    parts.append(ev_src)
     parts.append('#include "sde_kernel.cuh"')
     return ("\n".join(parts) + "\n", m, n_obs, block,
             stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile))
@@ -260,7 +285,7 @@ class SDESolver:
 
     # -- the hot path ------------------------------------------------------------------------
     def solve_many(self, problem: SDEProblem, n_trajectories=1, step_post_processing=None, seed=0, chunk_size=1,
-                   chunks_per_randomization=None, progress_bar=True, *, observables=None,
+                   chunks_per_randomization=None, progress_bar=True, *, observables=None, first_passage=None,
                    store_trajectories=True, traj_range=None, max_snapshots=None, prng_layout=None):
         """Integrate `n_trajectories` sample paths (reference `sde_solver.py:82-304`).
 
@@ -268,6 +293,10 @@ class SDESolver:
         observables        callable (x, w, t) -> vector; its per-trajectory values at the final time are
                            reduced on the device to sums / sums of squares (result key 'moments', shape
                            (n_obs, 2), plus 'count').
+        first_passage      callable (x, w, t) -> scalar event function; for every trajectory the first step after which
+                           it is positive is located by linear interpolation between the states before and after
+                           that step, on the device (result keys 'hit_flag', 'hit_time', 'hit_state'; the host
+                           post-processing of reference `examples/hit.py:40-58` without storing the trajectory).
         store_trajectories False: do not allocate or write the snapshot arrays (moments-only run).
         traj_range         (begin, count): integrate only this slice of the n_trajectories-wide key
                            fan-out (multi-GPU sharding; keys stay those of the full run).
@@ -278,8 +307,9 @@ class SDESolver:
         if scheme not in SCHEMES:
             raise ValueError(f"unknown scheme {scheme!r}; expected one of {SCHEMES}")
         if getattr(problem, "bead_ring", None) is not None and (problem.dimension > 24 or self.use_bead_kernel):
-            if step_post_processing is not None or observables is not None:
-                raise NotImplementedError("the bead-chain kernel supports neither step_post_processing nor observables")
+            if step_post_processing is not None or observables is not None or first_passage is not None:
+                raise NotImplementedError("the bead-chain kernel supports neither step_post_processing, observables "
+                                          "nor first_passage")
             return self._solve_bead_ring(problem, n_trajectories, seed, chunk_size, chunks_per_randomization,
                                          traj_range, max_snapshots, prng_layout)
         x0 = np.asarray(jnp._host(problem.x0))
@@ -310,7 +340,7 @@ class SDESolver:
                                                          n_snapshots=(n_snap if store_trajectories else 1),
                                                          snap_tile=self.snap_tile,
                                                          warp_specialize=self.warp_specialize,
-                                                         ws_tuning=self.ws_tuning)
+                                                         ws_tuning=self.ws_tuning, event=first_passage)
         traj_per_block = build_source.traj_per_block
         prog = runtime.load_program(source, "sde_solve_kernel")   # raises without a CUDA device
         torch = runtime.require_cuda()
@@ -337,6 +367,7 @@ class SDESolver:
             out_x = torch.empty((count, n_snap, d), dtype=tdt, device=dev)
             out_w = torch.empty((count, n_snap, m), dtype=tdt, device=dev)
         moments = torch.zeros((n_obs, 2), dtype=torch.float64, device=dev) if n_obs else None
+        out_hit = torch.empty((count, 2 + d), dtype=tdt, device=dev) if first_passage is not None else None
 
         ka, kb = prng_key(seed)
         args = runtime.SolveArgs(
@@ -347,7 +378,8 @@ class SDESolver:
             out_t=out_t.data_ptr() if out_t is not None else None,
             out_x=out_x.data_ptr() if out_x is not None else None,
             out_w=out_w.data_ptr() if out_w is not None else None,
-            moments=moments.data_ptr() if moments is not None else None)
+            moments=moments.data_ptr() if moments is not None else None,
+            out_hit=out_hit.data_ptr() if out_hit is not None else None)
         if count > 0:
             runtime.check(runtime.lib().sdeb200_solve(prog.handle, ctypes.byref(args), block, traj_per_block, dyn_smem,
                                                       runtime.current_stream_ptr()), "sdeb200_solve")
@@ -362,6 +394,10 @@ class SDESolver:
         if moments is not None:
             result["moments"] = DeviceArray(moments)
             result["count"] = count
+        if out_hit is not None:
+            result["hit_flag"] = DeviceArray(out_hit[:, 0] > 0.5)
+            result["hit_time"] = DeviceArray(out_hit[:, 1])
+            result["hit_state"] = DeviceArray(out_hit[:, 2:])
         return _Solution(result)
 
     def _solve_bead_ring(self, problem, n_trajectories, seed, chunk_size, chunks_per_randomization, traj_range,

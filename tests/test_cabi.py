@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts():
-    assert ctypes.sizeof(runtime.SolveArgs) == 112
+    assert ctypes.sizeof(runtime.SolveArgs) == 120 and runtime.SolveArgs.out_hit.offset == 112
     assert runtime.SolveArgs.n_traj_total.offset == 24 and runtime.SolveArgs.x0.offset == 48
     assert runtime.SolveArgs.dt.offset == 64 and runtime.SolveArgs.moments.offset == 104
     assert ctypes.sizeof(runtime.WienerArgs) == 56

@@ -138,3 +138,34 @@ def test_brownian_rotations_with_step_post_processing():
     _close64(got, ref, rtol=1e-7)          # 200 chaotic steps near the coordinate singularity amplify rounding
     angles = np.sqrt((np.asarray(got["solution_values"]) ** 2).sum(-1))
     assert angles.max() <= np.pi + 1e-9
+
+
+@pytest.mark.parametrize("scheme", ["euler", "wagner_platen"])
+def test_first_passage_observer_matches_host_post_processing(scheme):
+    """the hitting-time study of reference examples/hit.py (barrier y = r sin(phi) > 2) done on
+    the device, against the reference's own host-side process_trajectory logic applied to the stored trajectory."""
+    y_barrier = 2.0
+    prob, oprob = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    P.as_f64(prob, oprob)
+    dt = 2 ** -6
+    solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
+    event = lambda x, w, t: x[0] * jnp.sin(x[1]) - y_barrier
+    sol = solver.solve_many(prob, n_trajectories=200, seed=0, chunks_per_randomization=4, first_passage=event)
+    traj = np.asarray(sol["solution_values"])
+    tvals = np.asarray(sol["time_values"])
+    flag, ht, hx = (np.asarray(sol[k]) for k in ("hit_flag", "hit_time", "hit_state"))
+    y = traj[:, :, 0] * np.sin(traj[:, :, 1])
+    n_hit = 0
+    for i in range(200):
+        above = y[i] > y_barrier
+        assert bool(flag[i]) == bool(above.any())
+        if not above.any():
+            continue
+        k = int(above.argmax())
+        before = traj[i, k - 1] if k > 0 else np.asarray(prob.x0)
+        yb = y[i, k - 1] if k > 0 else prob.x0[0] * np.sin(prob.x0[1])
+        wgt = (y_barrier - yb) / (y[i, k] - yb)
+        assert np.allclose(hx[i], traj[i, k] * wgt + before * (1 - wgt), rtol=1e-9, atol=1e-12)
+        assert np.isclose(ht[i], (tvals[i, k] - dt) + wgt * dt, rtol=1e-9)
+        n_hit += 1
+    assert n_hit > 50          # drift 4 towards a barrier at distance 2: most paths hit within T = 1
