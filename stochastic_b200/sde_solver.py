@@ -18,6 +18,7 @@ round-up that overshoots tmax, dt**1.5 in Python double).
 """
 import ctypes
 from functools import wraps
+from typing import NamedTuple
 
 import numpy as np
 
@@ -30,6 +31,16 @@ from .trace import expr as E
 from .trace.taylor import SCHEMES, TracedProblem, step_expressions
 
 SCHEME_ID = {"euler": 0, "milstein": 1, "wagner_platen": 2}
+
+
+class KernelSource(NamedTuple):
+    """What `build_source` hands to the runtime: the translation unit and its launch geometry."""
+    source: str
+    noise_terms: int
+    n_obs: int
+    block: int              # threads per CTA (SDE_BLOCK)
+    dyn_smem_bytes: int
+    traj_per_block: int     # trajectories per CTA: block, or 128 for the warp-specialised kernel
 
 
 # ------------------------------------------------------------------------------------------
@@ -137,8 +148,7 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
                  event=None):
     """Trace the problem and emit the complete translation unit of its stepping kernel.
 
-    Returns (source, m, n_obs, block, dyn_smem_bytes); `build_source.traj_per_block` of the last call is the number
-    of trajectories per CTA (128 for the warp-specialised kernel, else block)."""
+    Returns a `KernelSource`."""
     E.trim_table()
     tp = TracedProblem(problem_a, problem_b, d)
     m = tp.m
@@ -189,10 +199,8 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
                                  [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
         parts += [post_src, obs_src, ev_src, '#include "sde_kernel_ws.cuh"']
-        build_source.traj_per_block = 128
-        return "\n".join(parts) + "\n", m, n_obs, ws_block, 2 * stage * 128 * elem
+        return KernelSource("\n".join(parts) + "\n", m, n_obs, ws_block, 2 * stage * 128 * elem, 128)
     block = runtime.pick_block(m, p, scheme, f64, block)
-    build_source.traj_per_block = block
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
         min_blocks = 2
@@ -238,8 +246,8 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     parts.append(obs_src)
     parts.append(ev_src)
     parts.append('#include "sde_kernel.cuh"')
-    return ("\n".join(parts) + "\n", m, n_obs, block,
-            stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile))
+    return KernelSource("\n".join(parts) + "\n", m, n_obs, block,
+                        stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile), block)
 
 
 class SDESolver:
@@ -333,7 +341,7 @@ class SDESolver:
         layout = prng_layout or config.get("prng_layout")
         chunk, n_chunks, cpr, n_frag = chunk_arithmetic(problem.tmax, self.dt, chunk_size, chunks_per_randomization)
         n_snap = n_chunks if max_snapshots is None else min(n_chunks, int(max_snapshots))
-        source, m, n_obs, block, dyn_smem = build_source(problem.a, problem.b, d, scheme, f64, layout,
+        source, m, n_obs, block, dyn_smem, traj_per_block = build_source(problem.a, problem.b, d, scheme, f64, layout,
                                                          post=step_post_processing, observe=observables,
                                                          block=self.block_size, min_blocks=self.min_blocks_per_sm,
                                                          lockstep=self.lockstep,
@@ -341,7 +349,6 @@ class SDESolver:
                                                          snap_tile=self.snap_tile,
                                                          warp_specialize=self.warp_specialize,
                                                          ws_tuning=self.ws_tuning, event=first_passage)
-        traj_per_block = build_source.traj_per_block
         prog = runtime.load_program(source, "sde_solve_kernel")   # raises without a CUDA device
         torch = runtime.require_cuda()
 

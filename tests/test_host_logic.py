@@ -320,12 +320,14 @@ def test_host_prng_matches_oracle():
 
 def test_warp_specialised_source_selection_and_register_budget():
     prob = workloads.polar_walk(4.0, (2.0, 0.0), f64=True)
-    src, m, n_obs, block, smem = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original")
-    assert "sde_kernel_ws.cuh" in src and block == 512 and smem == 2 * 46 * 128 * 8 and build_source.traj_per_block == 128
-    src, _, _, block, _ = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original", warp_specialize=False)
-    assert "sde_kernel_ws.cuh" not in src and block == 256 and build_source.traj_per_block == 256
-    src, _, _, block, _ = build_source(prob.a, prob.b, 2, "milstein", True, "original")
-    assert "sde_kernel_ws.cuh" not in src            # only Wagner-Platen with m > 1 stages its normals
+    ks = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original")
+    assert "sde_kernel_ws.cuh" in ks.source and ks.block == 512 and ks.dyn_smem_bytes == 2 * 46 * 128 * 8
+    assert ks.traj_per_block == 128 and ks.noise_terms == 2 and ks.n_obs == 0
+    ks = build_source(prob.a, prob.b, 2, "wagner_platen", True, "original", warp_specialize=False)
+    assert "sde_kernel_ws.cuh" not in ks.source and ks.block == 256 and ks.traj_per_block == 256
+    ks = build_source(prob.a, prob.b, 2, "milstein", True, "original")
+    assert "sde_kernel_ws.cuh" not in ks.source     # only Wagner-Platen with m > 1 stages its normals
+    assert "#define SDE_MIN_BLOCKS 6" in ks.source   # small step function: 80 registers, six CTAs per SM
     prob3, _ = P.coupled_3x3()
     src = build_source(prob3.a, prob3.b, 3, "wagner_platen", True, "original")[0]
     assert "sde_kernel_ws.cuh" not in src            # ring of 2 x 69 x 128 doubles does not fit twice per SM
