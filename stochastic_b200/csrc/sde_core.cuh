@@ -150,48 +150,73 @@ static __constant__ double ERFINV64_GE16[17] = {
     7.5995277030017761139e-05,  -0.00021503011930044477347, -0.00013871931833623122026, 1.0103004648645343977,
     4.8499064014085844221};
 
-// Lg1..Lg7 of fdlibm's e_log.c, then ln2_hi, ln2_lo
-static __constant__ double LOGC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                      2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                      1.479819860511658591e-01, 6.93147180369123816490e-01,
-                                      1.90821492927058770002e-10};
+// ln2 split so that k * ln2_hi is exact for every exponent k that can occur (21 trailing zero bits)
+static __constant__ double LOGC[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
+
+// 64-entry table for log(m), m in [1, 2): entry i = (1/c_i rounded to double, -log of that double) with
+// c_i = 1 + (i + 1/2)/64, generated with 60-digit arithmetic.  Global memory + read-only cache: the indices
+// are per-lane, which the constant cache would serialise.
+static __device__ const double2 SDE_LOGTAB[64] = {
+    {0.9922480620155039, 0.007782140442054963}, {0.9770992366412213, 0.023167059281534418},
+    {0.9624060150375939, 0.03831886430213666}, {0.9481481481481482, 0.05324451451881224},
+    {0.9343065693430657, 0.06795066190850778}, {0.920863309352518, 0.08244366921107454},
+    {0.9078014184397163, 0.09672962645855114}, {0.8951048951048951, 0.11081436634029011},
+    {0.8827586206896552, 0.12470347850095725}, {0.8707482993197279, 0.1384023228591192},
+    {0.8590604026845637, 0.151916042025842}, {0.847682119205298, 0.16524957289530717},
+    {0.8366013071895425, 0.17840765747281825}, {0.8258064516129032, 0.19139485299962947},
+    {0.8152866242038217, 0.20421554142869083}, {0.8050314465408805, 0.2168739383006143},
+    {0.7950310559006211, 0.2293741010648459}, {0.7852760736196319, 0.24171993688714513},
+    {0.7757575757575758, 0.25391520998096345}, {0.7664670658682635, 0.2659635484971379},
+    {0.757396449704142, 0.2778684510034563}, {0.7485380116959064, 0.2896332925830427},
+    {0.7398843930635838, 0.30126133057816185}, {0.7314285714285714, 0.3127557100038969},
+    {0.7231638418079096, 0.324119468654212}, {0.7150837988826816, 0.3353555419211378},
+    {0.7071823204419889, 0.3464667673462086}, {0.6994535519125683, 0.3574558889218038},
+    {0.6918918918918919, 0.36832556115870757}, {0.6844919786096256, 0.3790783529349695},
+    {0.6772486772486772, 0.38971675114002524}, {0.6701570680628273, 0.40024316412701266},
+    {0.6632124352331606, 0.4106599249852683}, {0.6564102564102564, 0.42096929464412963},
+    {0.649746192893401, 0.43117346481837143}, {0.6432160804020101, 0.4412745608048752},
+    {0.6368159203980099, 0.4512746441394586}, {0.6305418719211823, 0.46117571512217015},
+    {0.624390243902439, 0.470979715218791}, {0.6183574879227053, 0.48068852934575196},
+    {0.6124401913875598, 0.4903039880451939}, {0.6066350710900474, 0.49982786955644926},
+    {0.6009389671361502, 0.5092619017898079}, {0.5953488372093023, 0.5186077642080457},
+    {0.5898617511520737, 0.5278670896208424}, {0.5844748858447488, 0.5370414658968837},
+    {0.579185520361991, 0.5461324375981356}, {0.5739910313901345, 0.5551415075405016},
+    {0.5688888888888889, 0.564070138284803}, {0.5638766519823789, 0.5729197535617854},
+    {0.5589519650655022, 0.5816917396346225}, {0.5541125541125541, 0.5903874466021763},
+    {0.5493562231759657, 0.5990081896460834}, {0.5446808510638298, 0.6075552502245418},
+    {0.540084388185654, 0.616029877215514}, {0.5355648535564853, 0.6244332880118936},
+    {0.5311203319502075, 0.6327666695710378}, {0.5267489711934157, 0.6410311794209312},
+    {0.5224489795918368, 0.6492279466251097}, {0.5182186234817814, 0.65735807270836},
+    {0.5140562248995983, 0.6654226325450905}, {0.5099601593625498, 0.6734226752121667},
+    {0.5059288537549407, 0.6813592248079031}, {0.5019607843137255, 0.689233281238809},
+};
 
 // w = -log(1 - x^2) = -log1p(-x*x) for |x| < 1, branch-free.
 //
-// CUDA's log1p() takes one of two ~110-instruction paths depending on the argument, and the lanes of
-// a warp split evenly between them, so every normal paid for both.  Here t = 1 - x^2 is reduced to m in [sqrt(1/2), sqrt(2)) with integer ops on the exponent field, and
-// log(m) is evaluated with the classic s = f/(2+f) series (fdlibm's e_log.c scheme and its published
-// minimax coefficients Lg1..Lg7, |error| < 2^-58 on the reduced interval).  s only enters through a
-// second-order term, so an approximate reciprocal refined by two Newton steps replaces the division.
-// Absolute error of w is ~1e-16 (1 + w): indistinguishable from log1p's own last-place error.
+// CUDA's log1p() takes one of two ~110-instruction paths depending on the argument, and the lanes of a warp
+// split evenly between them, so every normal paid for both.  Here t = 1 - x^2 = 2^k m is split with integer
+// ops on the exponent field, m is reduced with one table entry (r = m / c_i - 1 as a single FMA, |r| < 2^-7)
+// and log(1 + r) is a degree-7 polynomial:  log t = k ln2 + log c_i + log1p(r).
+// Absolute error ~1e-16 for w <= 6.25 and relative error ~1e-16 beyond, which is all erf_inv's polynomial in w
+// can see (the result is as accurate as one obtained from log1p's correctly rounded w).
 __device__ __forceinline__ double neg_log_one_minus_sq(double x) {
     // x*x is rounded BEFORE the subtraction, exactly as in XLA's `-log1p(-x * x)`: near |x| = 1 the
     // result is ill-conditioned in x*x, so a fused 1 - x*x would change the far-tail normals.
     const double t = 1.0 - __dmul_rn(x, x);                 // in (0, 1], always a normal number
-    int hi = __double2hiint(t);
+    const int hi = __double2hiint(t);
     const int lo = __double2loint(t);
-    hi += 0x3ff00000 - 0x3fe6a09e;                          // shift the split point to sqrt(2)/2
-    const int k = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) + 0x3fe6a09e;
-    const double f = __hiloint2double(hi, lo) - 1.0;        // m - 1, m in [sqrt(1/2), sqrt(2))
-    const double d = 2.0 + f;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    const double s = f * r;
-    const double z = s * s;
-    const double z2 = z * z;
-    const double t1 = z2 * fma(z2, fma(z2, LOGC[5], LOGC[3]), LOGC[1]);
-    const double t2 = z * fma(z2, fma(z2, fma(z2, LOGC[6], LOGC[4]), LOGC[2]), LOGC[0]);
-    const double R = t2 + t1;
-    const double hfsq = 0.5 * f * f;
-    const double dk = (double)k;
-    // log(t) = k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f);  w = -log(t)
-    const double inner = (hfsq - fma(s, hfsq + R, dk * LOGC[8])) - f;
-    return fma(-dk, LOGC[7], inner);
+    const double dk = (double)((hi >> 20) - 1023);
+    const double2 e = __ldg(&SDE_LOGTAB[(hi >> 14) & 63]);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double r = fma(m, e.x, -1.0);
+    double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    q = fma(r, q, 0.2);
+    q = fma(r, q, -0.25);
+    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    const double p = fma(r * r, q, r);                      // log1p(r)
+    // w = -(k ln2_hi + (log c + (p + k ln2_lo)))
+    return fma(-dk, LOGC[0], -(e.y + fma(dk, LOGC[1], p)));
 }
 
 // erf_inv is split into the branch-free central polynomial (evaluated for a whole group of draws with
