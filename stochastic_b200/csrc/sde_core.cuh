@@ -658,8 +658,9 @@ struct WienerGen {
         constexpr int M = SDE_M, P = SDE_P;
         real xi[M], a[M], b[M];
         real zs[M][P + 1], es[M][P + 1];
+        real sa[M];                       // sum_r zs[j][r], reused by the C matrix
         {
-            real sa[M], sb[M];
+            real sb[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) { sa[j] = RC(0.0); sb[j] = RC(0.0); zs[j][0] = RC(0.0); es[j][0] = RC(0.0); }
             SDE_UNROLL
@@ -696,49 +697,51 @@ struct WienerGen {
             after_reads();
         }
 
-        // A (antisymmetric), B (symmetric)
-        real A[M][M], B[M][M];
+        // A (antisymmetric), B (symmetric); the zeta-zeta dot products are kept for C
+        real A[M][M], B[M][M], dzz[M][M];
 #pragma unroll
         for (int i = 0; i < M; ++i) {
 #pragma unroll
             for (int j = i; j < M; ++j) {
-                real sA = RC(0.0), sB = RC(0.0);
+                real sA = RC(0.0), sZ = RC(0.0), sE = RC(0.0);
                 SDE_UNROLL
                 for (int r = 1; r <= P; ++r) {
-                    sB = fma(zs[i][r], zs[j][r], sB);
-                    sB = fma(es[i][r], es[j][r], sB);
+                    sZ = fma(zs[i][r], zs[j][r], sZ);
+                    sE = fma(es[i][r], es[j][r], sE);
                     if (j > i) sA = fma((real)r * zs[i][r], es[j][r], fma(-(real)r * es[i][r], zs[j][r], sA));
                 }
-                B[i][j] = B[j][i] = (real)(0.25 / (SDE_PI * SDE_PI)) * sB;     // 1/(4 pi^2)
+                dzz[i][j] = dzz[j][i] = sZ;
+                B[i][j] = B[j][i] = (real)(0.25 / (SDE_PI * SDE_PI)) * (sZ + sE);     // 1/(4 pi^2)
                 A[i][j] = (real)(0.5 / SDE_PI) * sA;                // 1/(2 pi)
                 A[j][i] = -A[i][j];
             }
         }
 
         // C[j1][j2] = -1/(2 pi^2) sum_{l != r} [ r^2/(r^2-l^2) zs[j1][r] zs[j2][l] + r l/(r^2-l^2) es[j1][r] es[j2][l] ]
+        // Both kernels split into a constant and an antisymmetric part: r^2/(r^2-l^2) = 1/2 + (r^2+l^2)/(2(r^2-l^2)),
+        // r l/(r^2-l^2) = -(l r/(l^2-r^2)).  The constant part is 1/2 (S_j1 S_j2 - zs_j1 . zs_j2) with S_j = sum_r zs[j][r];
+        // the antisymmetric parts are sums over l < r of 2x2 determinants, change sign under j1 <-> j2 and vanish
+        // for j1 = j2 - so C costs one pass over the 45 pairs per unordered (j1, j2) instead of 2 x 90 terms per j1.
         real C[M][M];
 #pragma unroll
-        for (int j1 = 0; j1 < M; ++j1) {
-            real Uz[P + 1], Ue[P + 1];
-            SDE_UNROLL
-            for (int l = 1; l <= P; ++l) {
-                real uz = RC(0.0), ue = RC(0.0);
+        for (int i = 0; i < M; ++i) {
+            C[i][i] = -(real)(0.25 / (SDE_PI * SDE_PI)) * (sa[i] * sa[i] - dzz[i][i]);
+#pragma unroll
+            for (int j = i + 1; j < M; ++j) {
+                real asym = RC(0.0);
                 SDE_UNROLL
-                for (int r = 1; r <= P; ++r) {
-                    if (r != l) {
-                        uz = fma((real)(r * r) / (real)(r * r - l * l), zs[j1][r], uz);
-                        ue = fma((real)(r * l) / (real)(r * r - l * l), es[j1][r], ue);
+                for (int l = 1; l < P; ++l) {
+                    SDE_UNROLL
+                    for (int r = l + 1; r <= P; ++r) {
+                        const real dz = fma(-zs[i][l], zs[j][r], zs[i][r] * zs[j][l]);
+                        const real de = fma(-es[i][l], es[j][r], es[i][r] * es[j][l]);
+                        asym = fma((real)(r * r + l * l) / (real)(2 * (r * r - l * l)), dz, asym);
+                        asym = fma((real)(r * l) / (real)(r * r - l * l), de, asym);
                     }
                 }
-                Uz[l] = uz;
-                Ue[l] = ue;
-            }
-#pragma unroll
-            for (int j2 = 0; j2 < M; ++j2) {
-                real c = RC(0.0);
-                SDE_UNROLL
-                for (int l = 1; l <= P; ++l) c = fma(zs[j2][l], Uz[l], fma(es[j2][l], Ue[l], c));
-                C[j1][j2] = -(real)(0.5 / (SDE_PI * SDE_PI)) * c;
+                const real sym = RC(0.5) * (sa[i] * sa[j] - dzz[i][j]);
+                C[i][j] = -(real)(0.5 / (SDE_PI * SDE_PI)) * (sym + asym);
+                C[j][i] = -(real)(0.5 / (SDE_PI * SDE_PI)) * (sym - asym);
             }
         }
 
