@@ -37,10 +37,10 @@ N_TRAJ_PER_GPU = 10 ** 7
 TMAX = 1.0
 Y_DRIFT = 4.0
 FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10): the contract (algorithmic) figure
-# ncu counters of the warp-specialised kernel (profiles/r1_ncu_c2_ws_counters_2M_x128.csv): DFMA 3703, DMUL 664, DADD 364
+# ncu counters of the warp-specialised kernel (profiles/r1_ncu_c2_ws_counters_2M_x128.csv): DFMA 3214, DMUL 524, DADD 275
 # thread-instructions per trajectory-step; DRAM traffic of the dominant launch, 10^7 trajectories x 512 steps
 # (profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv): 42 MB read + 447 MB written (algorithmic: 400 MB of final states)
-EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3703 + 664 + 364
+EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3214 + 524 + 275
 DRAM_BYTES_PER_DOMINANT_LAUNCH = 42117632 + 446696448
 THEORETICAL_MEAN_PHI = 1.10714532096375
 
@@ -307,7 +307,7 @@ def run_b200(args):
                              "executed_tflops": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12,
                              "executed_frac": kernel_rate * EXECUTED_FLOPS_PER_TRAJ_STEP / 1e12 / fp64_peak,
                              "executed_note": "FP64 flops actually executed per trajectory-step (ncu DFMA x2 + DMUL + DADD "
-                                              "= 8434): the D/C-matrix factorisation does less work than the algorithmic "
+                                              "= 7227): the D/C-matrix factorisations and the table-based log do less work than the algorithmic "
                                               "count, so both fractions are reported",
                              "kernel": "sde_solve_kernel (dt=2^-9 launch)", "kernel_ms": ms_k,
                              "flops_per_trajectory_step": FLOPS_PER_TRAJ_STEP,
