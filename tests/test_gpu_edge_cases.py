@@ -169,3 +169,31 @@ def test_first_passage_observer_matches_host_post_processing(scheme):
         assert np.isclose(ht[i], (tvals[i, k] - dt) + wgt * dt, rtol=1e-9)
         n_hit += 1
     assert n_hit > 50          # drift 4 towards a barrier at distance 2: most paths hit within T = 1
+
+
+@pytest.mark.parametrize("n_steps", [1, 2, 3])
+@pytest.mark.parametrize("warp_specialize", [True, False])
+def test_very_short_runs_in_both_stepping_kernels(n_steps, warp_specialize):
+    """One, two and three steps in total: the producer/consumer ring of the warp-specialised kernel has two stages,
+    so these are exactly the cases where its empty/full hand-shake starts and ends."""
+    prob, oprob = P.polar_walk(4.0, (2.0, 0.0), 0.25)
+    P.as_f64(prob, oprob)
+    dt = 0.25 / n_steps
+    solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=dt)
+    solver.warp_specialize = warp_specialize
+    got = solver.solve_many(prob, n_trajectories=130, seed=8, chunk_size=None)     # 130: one full CTA + 2 trajectories
+    ref = osolver.solve_many(oprob, scheme="wagner_platen", dt=dt, n_trajectories=130, seed=8, chunk_size=None,
+                             dtype=np.float64)
+    _close64(got, ref)
+
+
+def test_both_stepping_kernels_agree_bit_for_bit():
+    prob, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    P.as_f64(prob)
+    out = []
+    for ws in (True, False):
+        solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=2 ** -5)
+        solver.warp_specialize = ws
+        out.append(solver.solve_many(prob, n_trajectories=777, seed=5, chunk_size=4, chunks_per_randomization=2))
+    for k in ("time_values", "solution_values", "wiener_values"):
+        assert np.array_equal(np.asarray(out[0][k]), np.asarray(out[1][k]))
