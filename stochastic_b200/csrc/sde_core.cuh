@@ -191,6 +191,8 @@ static __device__ const double2 SDE_LOGTAB[64] = {
     {0.5059288537549407, 0.6813592248079031}, {0.5019607843137255, 0.689233281238809},
 };
 
+static __constant__ double SDE_LOGPOLY[4] = {1.0 / 7.0, 0.2, 1.0 / 3.0, 1.4142135623730951};
+
 // w = -log(1 - x^2) = -log1p(-x*x) for |x| < 1, branch-free.
 //
 // CUDA's log1p() takes one of two ~110-instruction paths depending on the argument, and the lanes of a warp
@@ -209,10 +211,12 @@ __device__ __forceinline__ double neg_log_one_minus_sq(double x) {
     const double2 e = __ldg(&SDE_LOGTAB[(hi >> 14) & 63]);
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, e.x, -1.0);
-    double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-    q = fma(r, q, 0.2);
+    // literals whose low word is non-zero come from the constant bank (one operand of the FMA) instead of
+    // being rebuilt with two moves per use
+    double q = fma(r, SDE_LOGPOLY[0], -1.0 / 6.0);
+    q = fma(r, q, SDE_LOGPOLY[1]);
     q = fma(r, q, -0.25);
-    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, SDE_LOGPOLY[2]);
     q = fma(r, q, -0.5);
     const double p = fma(r * r, q, r);                      // log1p(r)
     // w = -(k ln2_hi + (log c + (p + k ln2_lo)))
@@ -296,7 +300,7 @@ __device__ __forceinline__ void normal_group(const Key (&key)[N], const u32 (&e)
     for (int i = 0; i < N; ++i) {
         real v = p[i] * x[i];
         if (!erfinv_is_central(w[i])) v = erfinv_tail(x[i], w[i]);
-        out[i] = 1.4142135623730951 * v;
+        out[i] = SDE_LOGPOLY[3] * v;
     }
 #else
 #pragma unroll

@@ -61,6 +61,8 @@ struct SolveArgs {   // identical to sde_kernel.cuh
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void st_shared(u32 addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_shared(u32 addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 }  // namespace sdeb
 
@@ -91,16 +93,19 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
         constexpr int PG = SDE_WS_PGROUPS;
         const int half = (threadIdx.x - NC) >> 7;              // producer warpgroup pg serves slots n = pg (mod PG)
         WienerGen gen;
-        u32 frag = 0xffffffffu;
-        for (u64 g = 0; g < total_steps; ++g) {
-            const u32 f = (u32)(g / S), s = (u32)(g % S);
-            if (f != frag) {
-                frag = f;
-                gen.init(split_key(tkey, A.n_fragments, f), S);
+        u32 f = 0, s = S;                                      // fragment number, step within the fragment
+        // shared-window byte address of this thread's first slot of stage 0; a running address per step keeps the
+        // store a single STS off one register instead of re-deriving the column every normal
+        const u32 col0 = (u32)__cvta_generic_to_shared(ring) + (u32)((half * NC + c) * sizeof(real));
+        constexpr u32 STAGE_BYTES = SDE_STAGE_COUNT * NC * sizeof(real), SLOT_BYTES = NC * sizeof(real);
+        for (u64 g = 0; g < total_steps; ++g, ++s) {
+            if (s == S) {                                      // first step of a fragment: re-randomise
+                s = 0;
+                gen.init(split_key(tkey, A.n_fragments, f++), S);
             }
             const int st = (int)(g & 1);
             if (g >= 2) bar_sync(EMPTY0 + st, ALL);            // consumers have drained this stage
-            real* const col = ring + (size_t)st * SDE_STAGE_COUNT * NC + c;
+            u32 dst = col0 + (u32)st * STAGE_BYTES;
             // this thread's slots: n = half, half + PG, ... ; SDE_WS_GROUP of them per iteration (independent chains)
             constexpr int G = SDE_WS_GROUP;
             constexpr int SERIES = 2 * SDE_P * SDE_M;             // zeta then eta, SDE_P * SDE_M each
@@ -122,7 +127,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                 }
                 normal_group<G>(kk, ee, ss, nn);
 #pragma unroll
-                for (int i = 0; i < G; ++i) col[slot[i] * NC] = nn[i];
+                for (int i = 0; i < G; ++i) st_shared(dst + (u32)(slot[i] - n) * SLOT_BYTES, nn[i]);
+                dst += PG * G * SLOT_BYTES;
             }
             {   // xi, mu, phi: 3 SDE_M slots, this thread takes those with its parity
                 constexpr int T = (3 * SDE_M + PG - 1) / PG;
@@ -140,8 +146,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                     ss[i] = S * SDE_M;
                 }
                 normal_group<T>(kk, ee, ss, nn);
+                const u32 tail = col0 + (u32)st * STAGE_BYTES - (u32)half * SLOT_BYTES;
 #pragma unroll
-                for (int i = 0; i < T; ++i) col[slot[i] * NC] = nn[i];
+                for (int i = 0; i < T; ++i) st_shared(tail + (u32)slot[i] * SLOT_BYTES, nn[i]);
             }
             __threadfence_block();
             bar_arrive(FULL0 + st, ALL);
