@@ -231,7 +231,10 @@ __device__ __forceinline__ double erfinv_w(double x) { return neg_log_one_minus_
 __device__ __forceinline__ bool erfinv_is_central(float w) { return w < 5.0f; }
 __device__ __forceinline__ bool erfinv_is_central(double w) { return w < 6.25; }
 
-static __device__ __noinline__ float erfinv_tail(float x, float w) {
+#ifndef SDE_TAIL_ATTR
+#define SDE_TAIL_ATTR __noinline__     // rarely taken: keep it out of the unrolled groups (override to __forceinline__)
+#endif
+static __device__ SDE_TAIL_ATTR float erfinv_tail(float x, float w) {
     w = sqrtf(w) - 3.0f;
     float p = ERFINV32_GE5[0];
 #pragma unroll 1
@@ -239,7 +242,7 @@ static __device__ __noinline__ float erfinv_tail(float x, float w) {
     return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7f800000) : p * x;
 }
 
-static __device__ __noinline__ double erfinv_tail(double x, double w) {
+static __device__ SDE_TAIL_ATTR double erfinv_tail(double x, double w) {
     double p;
     if (w < 16.0) {
         w = sqrt(w) - 3.25;
@@ -656,10 +659,12 @@ struct WienerGen {
 
     // -- staged normals -> iterated integrals of one step; `after_reads()` is invoked once every staged value
     //    has been copied into registers (the warp-specialised kernel releases the ring stage there)
-    template <class AfterReads>
+    //    The last CT of the 3M values (xi, mu, phi) may come from the caller's registers (`own`) instead of the stage.
+    template <int CT = 0, class AfterReads>
     __device__ __forceinline__ void wp_assemble(const StepScale& sc, Integrals& I, const real* stage,
-                                                AfterReads after_reads) const {
+                                                AfterReads after_reads, const real* own = nullptr) const {
         constexpr int M = SDE_M, P = SDE_P;
+#define SDE_TAIL(q) (((q) >= 3 * M - CT) ? own[(q) - (3 * M - CT)] : SDE_STAGE(2 * P * M + (q)))
         real xi[M], a[M], b[M];
         real zs[M][P + 1], es[M][P + 1];
         real sa[M];                       // sum_r zs[j][r], reused by the C matrix
@@ -692,9 +697,10 @@ struct WienerGen {
             const real two_sqrt_rho = RC(2.0) * sqrt(rho), sqrt_alpha = sqrt(alpha);
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                xi[j] = SDE_STAGE(2 * P * M + j);
-                const real mu = SDE_STAGE(2 * P * M + M + j);
-                const real phi = SDE_STAGE(2 * P * M + 2 * M + j);
+                xi[j] = SDE_TAIL(j);
+                const real mu = SDE_TAIL(M + j);
+                const real phi = SDE_TAIL(2 * M + j);
+#undef SDE_TAIL
                 a[j] = -(real)(1.4142135623730950488 / SDE_PI) * sa[j] - two_sqrt_rho * mu;   // sqrt(2)/pi
                 b[j] = fma((real)(1.0 / (1.4142135623730950488 * SDE_PI)), sb[j], sqrt_alpha * phi);  // 1/(sqrt(2) pi)
             }

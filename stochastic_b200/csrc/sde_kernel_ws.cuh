@@ -37,6 +37,9 @@
 #ifndef SDE_WS_PGROUPS
 #define SDE_WS_PGROUPS 2              // producer warpgroups per consumer warpgroup
 #endif
+#ifndef SDE_WS_CTAIL
+#define SDE_WS_CTAIL 0                // of the 3M normals xi, mu, phi: how many (the last ones) the consumer draws itself
+#endif
 #define SDE_WS_NC 128                 // consumer threads = trajectories per CTA
 #define SDE_WS_NP (128 * SDE_WS_PGROUPS)   // producer threads
 static_assert(SDE_BLOCK == SDE_WS_NC + SDE_WS_NP, "SDE_BLOCK must be 128 consumers + 128 per producer warpgroup");
@@ -110,6 +113,26 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             constexpr int G = SDE_WS_GROUP;
             constexpr int SERIES = 2 * SDE_P * SDE_M;             // zeta then eta, SDE_P * SDE_M each
             const u32 base = s * (u32)(SDE_P * SDE_M), size = S * (u32)(SDE_P * SDE_M);
+            if constexpr (G == 1) {
+                // one series after the other: the key is loop-invariant and the element index a running counter
+                int n = half;
+                u32 e = base + (u32)half;
+#pragma unroll 1
+                for (int ser = 0; ser < 2; ++ser) {
+                    const Key k = ser ? gen.k_eta : gen.k_zeta;
+                    const int end = (ser + 1) * SDE_P * SDE_M;
+#pragma unroll 1
+                    for (; n < end; n += PG, e += PG, dst += PG * SLOT_BYTES) st_shared(dst, normal_elem(k, e, size));
+                    e -= (u32)(SDE_P * SDE_M);
+                }
+                // then the xi, mu, phi slots the consumer does not draw itself, same round-robin
+#pragma unroll 1
+                for (; n < SERIES + 3 * SDE_M - SDE_WS_CTAIL; n += PG, dst += PG * SLOT_BYTES) {
+                    const int q = n - SERIES;
+                    const Key k = (q < SDE_M) ? gen.k_xi : ((q < 2 * SDE_M) ? gen.k_mu : gen.k_phi);
+                    st_shared(dst, normal_elem(k, s * SDE_M + (u32)(q % SDE_M), S * SDE_M));
+                }
+            } else
 #pragma unroll 1
             for (int n = half; n < SERIES; n += PG * G) {
                 Key kk[G];
@@ -130,7 +153,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                 for (int i = 0; i < G; ++i) st_shared(dst + (u32)(slot[i] - n) * SLOT_BYTES, nn[i]);
                 dst += PG * G * SLOT_BYTES;
             }
-            {   // xi, mu, phi: 3 SDE_M slots, this thread takes those with its parity
+            if constexpr (G != 1) {   // xi, mu, phi: 3 SDE_M slots, this thread takes those with its parity
+                static_assert(G == 1 || SDE_WS_CTAIL == 0, "consumer-drawn normals need SDE_WS_GROUP == 1");
                 constexpr int T = (3 * SDE_M + PG - 1) / PG;
                 Key kk[T];
                 u32 ee[T], ss[T];
@@ -183,18 +207,45 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 #pragma unroll
         for (int i = 0; i < SDE_D; ++i) hit_x[i] = RC(0.0);
 #endif
-        WienerGen gen;                                         // only S is used on this side
+        WienerGen gen;                                         // without consumer-drawn normals only S is used here
         gen.S = S;
         u32 snap = 0, in_chunk = 0;
+#if SDE_WS_CTAIL > 0
+        u32 f = 0, s = S;
+#endif
         for (u64 g = 0; g < total_steps; ++g) {
             const int st = (int)(g & 1);
+#if SDE_WS_CTAIL > 0
+            // the consumer's share of the step's normals, drawn while the producers finish theirs
+            if (s == S) {
+                s = 0;
+                gen.init(split_key(tkey, A.n_fragments, f++), S);
+            }
+            real own[SDE_WS_CTAIL];
+            {
+                constexpr int CT = SDE_WS_CTAIL;
+                Key kk[CT];
+                u32 ee[CT], ss[CT];
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {
+                    const int q = 3 * SDE_M - CT + i;
+                    kk[i] = (q < SDE_M) ? gen.k_xi : ((q < 2 * SDE_M) ? gen.k_mu : gen.k_phi);
+                    ee[i] = s * SDE_M + (u32)(q % SDE_M);
+                    ss[i] = S * SDE_M;
+                }
+                normal_group<CT>(kk, ee, ss, own);
+            }
+            ++s;
+#else
+            const real* own = nullptr;
+#endif
             bar_sync(FULL0 + st, ALL);                         // normals of step g are in the ring
             Integrals I;
             // the stage is released as soon as its values sit in registers (only if a producer will wait for it)
             const bool release = g + 2 < total_steps;
-            gen.wp_assemble(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c, [&] {
+            gen.wp_assemble<SDE_WS_CTAIL>(sc, I, ring + (size_t)st * SDE_STAGE_COUNT * NC + c, [&] {
                 if (release) bar_arrive(EMPTY0 + st, ALL);
-            });
+            }, own);
 #if SDE_HAS_EVENT
             real x_before[SDE_D];
 #pragma unroll

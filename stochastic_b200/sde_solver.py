@@ -168,7 +168,8 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
             "#define SDE_STAGE_STRIDE 128",
         ]
         # measured on B200 (profiles/README.md): 3 producer warpgroups per consumer warpgroup, one normal at a time
-        knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1}
+        knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1,
+                 "SDE_WS_CTAIL": 0}
         for knob, val in (ws_tuning or {}).items():
             if knob not in knobs:
                 raise KeyError(f"unknown warp-specialisation knob {knob!r}")
@@ -182,6 +183,11 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         parts.append(f"#define SDE_BLOCK {ws_block}")
         for knob, val in knobs.items():
             parts.append(f"#define {knob} {val}")
+        if knobs["SDE_WS_CTAIL"]:
+            if not 0 < knobs["SDE_WS_CTAIL"] <= 3 * m or knobs["SDE_WS_GROUP"] != 1:
+                raise ValueError("SDE_WS_CTAIL must be in [0, 3m] and needs SDE_WS_GROUP == 1")
+            # ptxas 12.9 crashes on a call to the out-of-line erf_inv tail from the register-grown consumer branch
+            parts.append("#define SDE_TAIL_ATTR __forceinline__")
         n_obs = 0
         post_src = obs_src = ""
         if post is not None:
