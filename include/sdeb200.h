@@ -99,6 +99,10 @@ int sdeb200_set_device(int device);
 int sdeb200_compile(const char* source, const char* include_dir, const char* arch,
                     void** cubin, size_t* cubin_size, char** log);
 void sdeb200_free(void* p);
+/* Which NVRTC sdeb200_compile uses (it is bound with dlopen: $SDEB200_NVRTC, then the CUDA toolkit's
+ * libnvrtc, then the soname - independent of what the host process loaded before).  `path` (optional)
+ * receives a pointer to a static string. */
+int sdeb200_nvrtc_version(int* major, int* minor, const char** path);
 
 /* Load a cubin on the current device and look up the kernel `entry`. */
 int sdeb200_program_load(const void* cubin, size_t cubin_size, const char* entry,

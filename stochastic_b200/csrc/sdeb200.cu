@@ -77,6 +77,68 @@ Driver& driver() {
     return d;
 }
 
+// ---- lazily bound NVRTC ----------------------------------------------------------------
+// Bound by dlopen, not at link time: a process that imported torch first already holds the NVRTC of torch's wheel
+// (an older minor version with the same soname), and which compiler builds the kernels must not depend on the
+// import order.  Preference: $SDEB200_NVRTC, the CUDA toolkit's copy, then whatever the soname resolves to.
+struct Nvrtc {
+    void* lib = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
+                                 const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    nvrtcResult (*Version)(int*, int*) = nullptr;
+    bool ok = false;
+    std::string why, path;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> candidates;
+        if (const char* e = getenv("SDEB200_NVRTC")) candidates.push_back(e);
+        if (const char* e = getenv("CUDA_HOME")) candidates.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+        candidates.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+        candidates.push_back("libnvrtc.so.12");
+        candidates.push_back("libnvrtc.so");
+        for (const std::string& c : candidates) {
+            n.lib = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (n.lib) {
+                n.path = c;
+                break;
+            }
+        }
+        if (!n.lib) {
+            n.why = "cannot load NVRTC (tried $SDEB200_NVRTC, $CUDA_HOME/lib64, /usr/local/cuda/lib64, libnvrtc.so.12)";
+            return;
+        }
+#define BIND(field, sym)                                              \
+    n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, sym)); \
+    if (!n.field) {                                                   \
+        n.why = std::string("missing NVRTC symbol ") + sym;           \
+        return;                                                       \
+    }
+        BIND(CreateProgram, "nvrtcCreateProgram")
+        BIND(CompileProgram, "nvrtcCompileProgram")
+        BIND(DestroyProgram, "nvrtcDestroyProgram")
+        BIND(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        BIND(GetProgramLog, "nvrtcGetProgramLog")
+        BIND(GetCUBINSize, "nvrtcGetCUBINSize")
+        BIND(GetCUBIN, "nvrtcGetCUBIN")
+        BIND(GetErrorString, "nvrtcGetErrorString")
+        BIND(Version, "nvrtcVersion")
+#undef BIND
+        n.ok = true;
+    });
+    return n;
+}
+
 std::string cu_err(CUresult r) {
     const char* s = nullptr;
     if (driver().ok) driver().GetErrorString(r, &s);
@@ -124,42 +186,56 @@ int sdeb200_compile(const char* source, const char* include_dir, const char* arc
     *cubin = nullptr;
     *cubin_size = 0;
     if (log) *log = nullptr;
+    Nvrtc& rt = nvrtc();
+    if (!rt.ok) return fail(2, rt.why);
     nvrtcProgram prog;
-    nvrtcResult r = nvrtcCreateProgram(&prog, source, "sde_problem.cu", 0, nullptr, nullptr);
-    if (r != NVRTC_SUCCESS) return fail(2, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
+    nvrtcResult r = rt.CreateProgram(&prog, source, "sde_problem.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(2, std::string("nvrtcCreateProgram: ") + rt.GetErrorString(r));
     std::string a = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
     std::string inc = std::string("--include-path=") + (include_dir ? include_dir : ".");
     std::vector<const char*> opts = {a.c_str(), inc.c_str(), "--std=c++17", "-lineinfo", "--fmad=true",
                                      "-default-device"};
-    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    r = rt.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t log_size = 0;
-    nvrtcGetProgramLogSize(prog, &log_size);
+    rt.GetProgramLogSize(prog, &log_size);
     std::string log_text(log_size, '\0');
-    if (log_size > 1) nvrtcGetProgramLog(prog, &log_text[0]);
+    if (log_size > 1) rt.GetProgramLog(prog, &log_text[0]);
     if (log && log_size > 1) {
         *log = (char*)malloc(log_size + 1);
         memcpy(*log, log_text.c_str(), log_size);
         (*log)[log_size] = 0;
     }
     if (r != NVRTC_SUCCESS) {
-        nvrtcDestroyProgram(&prog);
-        return fail(2, std::string("nvrtcCompileProgram: ") + nvrtcGetErrorString(r) + "\n" + log_text);
+        rt.DestroyProgram(&prog);
+        return fail(2, std::string("nvrtcCompileProgram: ") + rt.GetErrorString(r) + "\n" + log_text);
     }
     size_t n = 0;
-    r = nvrtcGetCUBINSize(prog, &n);
+    r = rt.GetCUBINSize(prog, &n);
     if (r != NVRTC_SUCCESS || n == 0) {
-        nvrtcDestroyProgram(&prog);
-        return fail(2, std::string("nvrtcGetCUBINSize: ") + nvrtcGetErrorString(r));
+        rt.DestroyProgram(&prog);
+        return fail(2, std::string("nvrtcGetCUBINSize: ") + rt.GetErrorString(r));
     }
     void* buf = malloc(n);
-    r = nvrtcGetCUBIN(prog, (char*)buf);
-    nvrtcDestroyProgram(&prog);
+    r = rt.GetCUBIN(prog, (char*)buf);
+    rt.DestroyProgram(&prog);
     if (r != NVRTC_SUCCESS) {
         free(buf);
-        return fail(2, std::string("nvrtcGetCUBIN: ") + nvrtcGetErrorString(r));
+        return fail(2, std::string("nvrtcGetCUBIN: ") + rt.GetErrorString(r));
     }
     *cubin = buf;
     *cubin_size = n;
+    return 0;
+}
+
+int sdeb200_nvrtc_version(int* major, int* minor, const char** path) {
+    Nvrtc& rt = nvrtc();
+    if (!rt.ok) return fail(2, rt.why);
+    int ma = 0, mi = 0;
+    nvrtcResult r = rt.Version(&ma, &mi);
+    if (r != NVRTC_SUCCESS) return fail(2, std::string("nvrtcVersion: ") + rt.GetErrorString(r));
+    if (major) *major = ma;
+    if (minor) *minor = mi;
+    if (path) *path = rt.path.c_str();
     return 0;
 }
 

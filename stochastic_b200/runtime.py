@@ -19,6 +19,7 @@ EXPORTS = (
     "sdeb200_abi_version", "sdeb200_last_error", "sdeb200_set_device", "sdeb200_compile", "sdeb200_free",
     "sdeb200_program_load", "sdeb200_program_destroy", "sdeb200_program_info", "sdeb200_solve",
     "sdeb200_wiener_integrals", "sdeb200_keys_split", "sdeb200_normal", "sdeb200_fp64_peak", "sdeb200_bead_solve",
+    "sdeb200_nvrtc_version",
 )
 
 
@@ -106,6 +107,8 @@ def lib():
                                      ctypes.c_void_p, ctypes.c_void_p]
         L.sdeb200_fp64_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.sdeb200_set_device.argtypes = [ctypes.c_int]
+        L.sdeb200_nvrtc_version.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                            ctypes.POINTER(ctypes.c_char_p)]
         _lib = L
     return _lib
 
@@ -172,8 +175,16 @@ def current_stream_ptr():
 # ------------------------------------------------------------------------------------------
 # compile + cache
 # ------------------------------------------------------------------------------------------
+def nvrtc_version():
+    """(major, minor, path) of the NVRTC the library compiles with (the CUDA toolkit's, not the host process's)."""
+    major, minor, path = ctypes.c_int(), ctypes.c_int(), ctypes.c_char_p()
+    check(lib().sdeb200_nvrtc_version(ctypes.byref(major), ctypes.byref(minor), ctypes.byref(path)), "NVRTC")
+    return major.value, minor.value, (path.value or b"").decode()
+
+
 def _core_fingerprint():
     h = hashlib.sha256()
+    h.update("nvrtc %d.%d\n".encode() % nvrtc_version()[:2])      # cubins of different compilers never mix
     for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh", "sde_bead_kernel.cuh"):
         with open(os.path.join(CSRC_DIR, name), "rb") as f:
             h.update(f.read())

@@ -23,11 +23,19 @@ def _declared_functions():
 def test_library_exports_every_declared_symbol():
     lib = runtime.lib()
     names = _declared_functions()
-    assert len(names) >= 13
+    assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sdeb200.h but not exported"
     assert set(names) == set(runtime.EXPORTS)
     assert lib.sdeb200_abi_version() == 1
+
+
+def test_nvrtc_is_bound_independently_of_the_host_process():
+    import torch  # noqa: F401  (its wheel ships an older NVRTC under the same soname)
+    major, minor, path = runtime.nvrtc_version()
+    assert major >= 12 and path
+    if os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12") and not os.environ.get("SDEB200_NVRTC"):
+        assert path.startswith(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
 
 
 def test_struct_layouts():
