@@ -191,7 +191,20 @@ static __device__ const double2 SDE_LOGTAB[64] = {
     {0.5059288537549407, 0.6813592248079031}, {0.5019607843137255, 0.689233281238809},
 };
 
-static __constant__ double SDE_LOGPOLY[4] = {1.0 / 7.0, 0.2, 1.0 / 3.0, 1.4142135623730951};
+static __constant__ double SDE_LOGPOLY[6] = {1.0 / 7.0, 0.2, 1.0 / 3.0, 1.4142135623730951, -1.0 / 6.0,
+                                            -0.99999999999999988898 /* nextafter(-1, 0) */};
+
+#ifndef SDE_LOGTAB_IN_SMEM
+#define SDE_LOGTAB_IN_SMEM 0           // kernels that set this call sde_fill_logtab() before the first draw
+#endif
+#if SDE_LOGTAB_IN_SMEM
+__shared__ double2 sde_logtab_smem[64];
+// all threads of the CTA, before any normal is drawn (contains a __syncthreads)
+__device__ __forceinline__ void sde_fill_logtab() {
+    if (threadIdx.x < 64) sde_logtab_smem[threadIdx.x] = SDE_LOGTAB[threadIdx.x];
+    __syncthreads();
+}
+#endif
 
 // w = -log(1 - x^2) = -log1p(-x*x) for |x| < 1, branch-free.
 //
@@ -208,7 +221,11 @@ __device__ __forceinline__ double neg_log_one_minus_sq(double x) {
     const int hi = __double2hiint(t);
     const int lo = __double2loint(t);
     const double dk = (double)((hi >> 20) - 1023);
+#if SDE_LOGTAB_IN_SMEM
+    const double2 e = sde_logtab_smem[(hi >> 14) & 63];     // 32-bit shared address: two integer ops fewer per draw
+#else
     const double2 e = __ldg(&SDE_LOGTAB[(hi >> 14) & 63]);
+#endif
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, e.x, -1.0);
     // literals whose low word is non-zero come from the constant bank (one operand of the FMA) instead of
@@ -261,11 +278,12 @@ static __device__ SDE_TAIL_ATTR double erfinv_tail(double x, double w) {
 // jax.random.uniform(key, shape, dtype, nextafter(-1,0), 1) for one element, then
 // jax.random.normal = sqrt(2) * erf_inv(u)
 __device__ __forceinline__ double uniform_pm1(u64 bits) {
-    const double lo = -0.99999999999999988898;  // nextafter(-1, 0)
     double f = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)) - 1.0;
     // jax clamps with max(lo, .) against rounding below lo; here hi - lo rounds to exactly 2, f * 2 is exact and
-    // f >= 0, so f * 2 + lo >= lo already holds after rounding and the clamp is the identity
-    return fma(f, 2.0, lo);
+    // f >= 0, so f * 2 + lo >= lo already holds after rounding and the clamp is the identity.
+    // (One FMA on purpose: the producers of the warp-specialised kernel run one dependent chain per warp, and
+    // splitting this or the first Horner step of the log into mul + add to save the literal moves cost 4 %.)
+    return fma(f, 2.0, SDE_LOGPOLY[5]);
 }
 
 __device__ __forceinline__ float uniform_pm1(u32 bits) {

@@ -64,6 +64,9 @@ extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
 
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solve_kernel(const sdeb::SolveArgs A) {
     using namespace sdeb;
+#if SDE_LOGTAB_IN_SMEM
+    sde_fill_logtab();
+#endif
     real* const stage = reinterpret_cast<real*>(sde_dyn_smem) + threadIdx.x;
 #if SDE_SNAP_TILE > 1
     // Snapshot staging: the thread-per-trajectory mapping would store 8 bytes at a stride of a whole trajectory

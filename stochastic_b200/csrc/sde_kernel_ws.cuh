@@ -89,6 +89,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
     root.a = A.key_a;
     root.b = A.key_b;
     const Key tkey = split_key(root, A.n_traj_total, A.traj_begin + tid);
+#if SDE_LOGTAB_IN_SMEM
+    sde_fill_logtab();
+#endif
 
     if (!is_consumer) {
         // ================================ producers =====================================================

@@ -16,6 +16,7 @@ t=0) and error behaviour.  What changes is everything underneath:
 Host-side integer/float arithmetic follows the reference exactly (`int(tmax/dt)`, the chunk
 round-up that overshoots tmax, dt**1.5 in Python double).
 """
+import os
 import ctypes
 from functools import wraps
 from typing import NamedTuple
@@ -169,7 +170,7 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         ]
         # measured on B200 (profiles/README.md): 3 producer warpgroups per consumer warpgroup, one normal at a time
         knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1,
-                 "SDE_WS_CTAIL": 0}
+                 "SDE_WS_CTAIL": 0, "SDE_LOGTAB_IN_SMEM": 1}
         for knob, val in (ws_tuning or {}).items():
             if knob not in knobs:
                 raise KeyError(f"unknown warp-specialisation knob {knob!r}")
