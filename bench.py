@@ -37,11 +37,11 @@ N_TRAJ_PER_GPU = 10 ** 7
 TMAX = 1.0
 Y_DRIFT = 4.0
 FLOPS_PER_TRAJ_STEP = 10.9e3          # SURVEY.md 8(d), C2/C5 Wagner-Platen (m=2, p=10): the contract (algorithmic) figure
-# ncu counters of the warp-specialised kernel (profiles/r1_ncu_c2_ws_counters_2M_x128.csv): DFMA 3214, DMUL 524, DADD 275
+# ncu counters of the warp-specialised kernel (profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv): DFMA 3212, DMUL 524, DADD 275
 # thread-instructions per trajectory-step; DRAM traffic of the dominant launch, 10^7 trajectories x 512 steps
-# (profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv): 42 MB read + 447 MB written (algorithmic: 400 MB of final states)
-EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3214 + 524 + 275
-DRAM_BYTES_PER_DOMINANT_LAUNCH = 42117632 + 446696448
+# (profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv): 94 MB read + 478 MB written (algorithmic: 400 MB of final states)
+EXECUTED_FLOPS_PER_TRAJ_STEP = 2 * 3212 + 524 + 275
+DRAM_BYTES_PER_DOMINANT_LAUNCH = 94166784 + 477996032
 THEORETICAL_MEAN_PHI = 1.10714532096375
 
 
