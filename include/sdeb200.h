@@ -111,19 +111,23 @@ int sdeb200_program_destroy(sdeb200_program_t* prog);
 /* Registers per thread / static shared memory of the loaded kernel (diagnostics). */
 int sdeb200_program_info(sdeb200_program_t* prog, int* regs, int* smem_bytes, int* max_threads);
 
-/* Launch the stepping kernel: `block` threads per CTA (must equal the SDE_BLOCK the program was compiled
+/* Launch the stepping kernel - replaces `jax.vmap(get_solution)(keys, initial_conditions)`,
+ * pychastic/sde_solver.py:288-300, i.e. the scan nest :228-286 for every trajectory of the launch.
+ * `block` threads per CTA (must equal the SDE_BLOCK the program was compiled
  * with), `traj_per_block` trajectories per CTA (0 = block: one thread per trajectory; 128 for the
- * warp-specialised variant whose 384-thread CTAs hold 128 consumer + 256 producer threads),
+ * warp-specialised variant whose 512-thread CTAs hold 128 consumer + 384 producer threads),
  * `dyn_smem_bytes` of dynamic shared memory (the staging area of the in-kernel normal generator). */
 int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int block, int traj_per_block,
                   size_t dyn_smem_bytes, void* stream);
 
-/* Launch the bead-chain kernel (entry `sde_bead_kernel`): one CTA of `block` threads per trajectory, at most
+/* Launch the bead-chain kernel (entry `sde_bead_kernel`) - the same dispatch for the drift / noise functors of
+ * examples/example_writhed_dna_loop.py:49-74 (RPY mobility, Cholesky noise): one CTA of `block` threads per trajectory, at most
  * `max_ctas` CTAs (grid-stride over trajectories; 0 = one CTA per trajectory). */
 int sdeb200_bead_solve(sdeb200_program_t* prog, const sdeb200_bead_args_t* args, int block,
                        size_t dyn_smem_bytes, unsigned max_ctas, void* stream);
 
-/* Launch the unit-step Wiener-integral generator kernel (one thread per step). */
+/* Launch the unit-step Wiener-integral generator kernel (one thread per step) - replaces
+ * get_wiener_integrals, pychastic/vectorized_I_generation.py:243-473. */
 int sdeb200_wiener_integrals(sdeb200_program_t* prog, const sdeb200_wiener_args_t* args, int block,
                              size_t dyn_smem_bytes, void* stream);
 
