@@ -9,6 +9,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 prob = workloads.dna_loop(n_beads=40, tmax=(steps + 0.5) * 1e-7, f64=True)
 solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+if os.environ.get("BLOCK"):
+    solver.block_size = int(os.environ["BLOCK"])
 for _ in range(2):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -434,6 +434,10 @@ class SDESolver:
         d = 3 * nb
         layout = prng_layout or config.get("prng_layout")
         block = max(128, -(-d // 32) * 32)
+        if self.block_size:
+            if self.block_size % 32 or not block <= self.block_size <= 1024:
+                raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
+            block = int(self.block_size)
         source = "\n".join([
             "// generated by stochastic_b200.sde_solver (bead-chain functor)",
             f"#define SDE_NB {nb}", f"#define SDE_F64 {1 if f64 else 0}",
