@@ -15,9 +15,11 @@ Parity status
   trajectories (`tests/golden/stopping_time_trajectory_*.csv`,
   `tests/golden/bead_single_trajectory_head.csv`; see `tests/test_oracle_golden.py`).
 * threefry2x32 / key splitting: PINNED by Random123 and JAX known-answer values.
-* fp64 stream (64 random bits per draw): parity unpinned by an external fixture - JAX
-  cannot be installed here.  It shares every code path with the pinned fp32 twin except
-  the documented 64-bit counter layout of `jax._src.prng._threefry_random_bits_original`.
+* fp64 stream (64 random bits per draw): the BITS are pinned by jax's own regression vectors
+  for `random_bits(key(1701), 64, (3,))` (jax tests/random_test.py::testRngRandomBits, with and
+  without x64); the map bits -> uniform -> normal shares its code with the pinned fp32 twin
+  (52 instead of 23 mantissa bits, XLA's f64 `erf_inv` polynomial checked against scipy).  No
+  fp64 TRAJECTORY fixture exists - JAX cannot be installed here.
 * Wagner-Platen stepping: pinned only statistically (iterated-integral moments against
   `wiener_integral_moments.E/E2`, strong/weak orders), as in the reference's own tests.
 """

@@ -30,8 +30,23 @@ def test_jax_key_known_answers():
     assert jax_prng.random_bits(K0, 32, (3,)).tolist() == [4146024105, 1351547692, 2718843009]
     n = jax_prng.normal(K0, (3,), np.float32)
     assert np.allclose(n, [1.8160863, -0.48262316, 0.33988908], atol=2e-7)
+    # jax tests/random_test.py::testPRNGValues
+    assert jax_prng.split(K0, 4).tolist() == [[2285895361, 1501764800], [1518642379, 4090693311],
+                                              [433833334, 4221794875], [839183663, 3740430601]]
+    assert jax_prng.fold_in(K0, 4).tolist() == [2285895361, 433833334]
     chain = jax_prng.split(jax_prng.split(K0, 5)[0], 2048)[0]
     assert chain.tolist() == [3338368460, 4177929024]
+
+
+def test_jax_random_bits_known_answers_32_and_64():
+    """jax's own regression vectors (jax tests/random_test.py::testRngRandomBits, key 1701, threefry, x64 enabled):
+    the 64-bit case is what pins the counter layout of the fp64 stream."""
+    key = jax_prng.PRNGKey(1701)
+    assert jax_prng.random_bits(key, 32, (3,)).tolist() == [56197195, 4200222568, 961309823]
+    assert jax_prng.random_bits(key, 64, (3,)).tolist() == [3982329540505020460, 16822122385914693683,
+                                                            7882654074788531506]
+    # the same test's expectation with x64 disabled is the truncation of those words to 32 bits
+    assert [b & 0xFFFFFFFF for b in jax_prng.random_bits(key, 64, (3,)).tolist()] == [676898860, 3164047411, 4010691890]
 
 
 def test_erfinv_against_scipy():
