@@ -34,6 +34,10 @@ def test_jax_key_known_answers():
     assert jax_prng.split(K0, 4).tolist() == [[2285895361, 1501764800], [1518642379, 4090693311],
                                               [433833334, 4221794875], [839183663, 3740430601]]
     assert jax_prng.fold_in(K0, 4).tolist() == [2285895361, 433833334]
+    # scalar draws printed in jax's documentation (random-numbers tutorial, `jax.random` module docs)
+    assert abs(float(jax_prng.uniform(K0, (1,), np.float32)[0]) - 0.41845703) < 1e-8
+    assert abs(float(jax_prng.normal(K0, (1,), np.float32)[0]) - (-0.20584226)) < 2e-8
+    assert abs(float(jax_prng.normal(jax_prng.PRNGKey(42), (1,), np.float32)[0]) - (-0.18471177)) < 2e-8
     chain = jax_prng.split(jax_prng.split(K0, 5)[0], 2048)[0]
     assert chain.tolist() == [3338368460, 4177929024]
 
