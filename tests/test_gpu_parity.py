@@ -58,6 +58,22 @@ def test_normal_stream(n, dtype, layout):
     assert np.all(np.abs(got - ref) <= 8 * eps * np.maximum(np.abs(ref), 0.25))
 
 
+def test_fp64_normals_from_jax_pinned_bits():
+    """The three 64-bit words jax's own regression test pins for key 1701 (tests/test_oracle_golden.py), mapped to
+    uniforms and normals on the host, against the device stream for the same key."""
+    bits = np.array([3982329540505020460, 16822122385914693683, 7882654074788531506], dtype=np.uint64)
+    lo = np.nextafter(-1.0, 0.0)
+    f = ((bits >> np.uint64(12)) | np.uint64(0x3FF0000000000000)).view(np.float64) - 1.0
+    u = np.maximum(lo, f * 2.0 + lo)
+    from scipy.special import erfinv
+    ref = np.sqrt(2.0) * erfinv(u)
+    key = jax_prng.PRNGKey(1701)
+    out = torch.empty(3, dtype=torch.float64, device="cuda")
+    runtime.check(runtime.lib().sdeb200_normal(int(key[0]), int(key[1]), 3, 1, 0, out.data_ptr(),
+                                               runtime.current_stream_ptr()), "normal")
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-14, atol=1e-15)
+
+
 def _cmp_integrals(got, ref, tol):
     assert set(got) == set(ref)
     for k in ref:
