@@ -412,7 +412,9 @@ class SDESolver:
             result["hit_flag"] = DeviceArray(out_hit[:, 0] > 0.5)
             result["hit_time"] = DeviceArray(out_hit[:, 1])
             result["hit_state"] = DeviceArray(out_hit[:, 2:])
-        return _Solution(result)
+        sol = _Solution(result)
+        sol._keepalive = (x0_dev,)        # the launch is asynchronous: its inputs live as long as its results
+        return sol
 
     def _solve_bead_ring(self, problem, n_trajectories, seed, chunk_size, chunks_per_randomization, traj_range,
                          max_snapshots, prng_layout):
@@ -476,8 +478,10 @@ class SDESolver:
         runtime.STATS["launches"] += 1
         self.last_program = prog
         self.last_steps = n_snap * chunk
-        return _Solution(dict(time_values=DeviceArray(out_t), solution_values=DeviceArray(out_x),
-                              wiener_values=DeviceArray(out_w)))
+        sol = _Solution(dict(time_values=DeviceArray(out_t), solution_values=DeviceArray(out_x),
+                             wiener_values=DeviceArray(out_w)))
+        sol._keepalive = (x0_dev,)
+        return sol
 
     def solve(self, problem, seed=0, chunk_size=1, chunks_per_randomization=None, progress_bar=True):
         """One trajectory, leading axis stripped (reference `sde_solver.py:306-359`)."""
