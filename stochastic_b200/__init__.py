@@ -22,6 +22,9 @@ from . import sde_solver  # noqa: F401
 from . import vectorized_I_generation  # noqa: F401
 from . import wiener_integral_moments  # noqa: F401
 from .autodiff import grad, hessian, jacobian  # noqa: F401
+from . import hostutil as tree_util  # noqa: F401  (tree_util.tree_map)
+from .hostutil import jit, vmap  # noqa: F401  (host-side stand-ins for post-processing code, see hostutil.py)
+from . import prng as random  # noqa: F401  (random.PRNGKey / split / fold_in, host side)
 
 # `import stochastic_b200.numpy as jnp` mirrors `import jax.numpy as jnp`
 _sys.modules[__name__ + ".numpy"] = jnp

@@ -268,7 +268,10 @@ for _name in ("reshape", "transpose", "swapaxes", "moveaxis", "roll", "tile", "r
               "allclose", "all", "any", "cumprod", "sort", "argsort", "histogram", "nonzero", "count_nonzero",
               "logical_xor", "rint", "round", "ceil", "hypot", "deg2rad", "rad2deg", "nan_to_num", "array_equal",
               "split", "hstack", "vstack", "atleast_1d", "atleast_2d", "issubdtype", "floating", "integer",
-              "savetxt", "loadtxt", "empty", "empty_like", "copy", "unique", "interp", "kron", "cross"):
+              "savetxt", "loadtxt", "empty", "empty_like", "copy", "unique", "interp", "kron", "cross",
+              "ediff1d", "pad", "diff", "cov", "corrcoef", "average", "nanmean", "nanstd", "histogram2d", "digitize",
+              "searchsorted", "bincount", "gradient", "trapezoid", "convolve", "polyfit", "polyval", "append",
+              "insert", "delete", "column_stack", "dstack", "array_split", "flipud", "fliplr", "rot90", "linalg"):
     if hasattr(_np, _name) and _name not in globals():
         obj = getattr(_np, _name)
         globals()[_name] = _passthrough(_name) if callable(obj) and not isinstance(obj, type) else obj

@@ -336,3 +336,31 @@ def test_warp_specialised_source_selection_and_register_budget():
                      ws_tuning={"SDE_WS_CONSUMER_REGS": 120, "SDE_WS_PRODUCER_REGS": 48})
     with pytest.raises(KeyError):
         build_source(prob.a, prob.b, 2, "wagner_platen", True, "original", ws_tuning={"NOPE": 1})
+
+
+def test_host_side_stand_ins_for_post_processing_code():
+    """`vmap` / `jit` / `tree_util.tree_map` and the numpy pass-throughs the reference's example scripts apply to
+    result arrays (reference examples/hit.py:40-61, examples/jfm.py:134-203)."""
+    import stochastic_b200 as jax
+
+    def process_trajectory(traj):                       # shaped like examples/hit.py::process_trajectory
+        hit = jnp.argmax(traj[:, 0] > 1.5)
+        return {"hit_index": hit, "hit_place": traj[hit], "path_length": jnp.sum(jnp.abs(jnp.diff(traj[:, 0])))}
+
+    rng = np.random.default_rng(0)
+    trajs = np.cumsum(rng.normal(size=(6, 50, 2)), axis=1)
+    out = jax.vmap(process_trajectory)(trajs)
+    assert out["hit_index"].shape == (6,) and out["hit_place"].shape == (6, 2)
+    for i in range(6):
+        ref = process_trajectory(trajs[i])
+        assert out["hit_index"][i] == ref["hit_index"] and np.array_equal(out["hit_place"][i], ref["hit_place"])
+        assert np.isclose(out["path_length"][i], ref["path_length"])
+    nested = jax.vmap(jax.vmap(lambda q: jnp.outer(q, q)))(np.ones((2, 5, 3)))
+    assert nested.shape == (2, 5, 3, 3)
+    assert np.array_equal(jax.vmap(lambda a, b: a * b, in_axes=(0, None))(np.arange(3.0), 2.0), [0.0, 2.0, 4.0])
+    assert jax.jit(process_trajectory) is process_trajectory and jax.jit(static_argnums=0)(len) is len
+    assert jax.tree_util.tree_map(lambda x: 2 * x, {"a": 1, "b": [2, 3]}) == {"a": 2, "b": [4, 6]}
+    msd = np.array([0.0, 1.0, 3.0])
+    assert np.array_equal(jnp.ediff1d(msd, to_end=float("nan"))[:2], [1.0, 2.0])
+    assert jnp.cov(rng.normal(size=(3, 40))).shape == (3, 3)
+    assert jnp.pad(np.ones((2, 2)), ((0, 0), (0, 2))).shape == (2, 4)
