@@ -511,8 +511,26 @@ struct WienerGen {
 #endif
 #elif SDE_SCHEME == SDE_EULER
 #if SDE_STAGE_COUNT > 0
+        {
+            // rolled loop over groups of G independent draws (G = 4, 3 or 2 when it divides M): the dependent
+            // threefry / Horner chains of a group interleave, the loop body stays small
+#ifndef SDE_EULER_GROUP
+#define SDE_EULER_GROUP ((SDE_M % 4 == 0) ? 4 : ((SDE_M % 3 == 0) ? 3 : ((SDE_M % 2 == 0) ? 2 : 1)))
+#endif
+            constexpr int G = SDE_EULER_GROUP;
+            static_assert(SDE_M % G == 0, "SDE_EULER_GROUP must divide SDE_M");
 #pragma unroll 1
-        for (int j = 0; j < SDE_M; ++j) SDE_STAGE(j) = normal_elem(k0, s0 * SDE_M + j, S * SDE_M);
+            for (int j = 0; j < SDE_M; j += G) {
+                Key kk[G];
+                u32 ee[G], ss[G];
+                real nn[G];
+#pragma unroll
+                for (int q = 0; q < G; ++q) { kk[q] = k0; ee[q] = s0 * SDE_M + j + q; ss[q] = S * SDE_M; }
+                normal_group<G>(kk, ee, ss, nn);
+#pragma unroll
+                for (int q = 0; q < G; ++q) SDE_STAGE(j + q) = nn[q];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < SDE_M; ++j) I[0].dW[j] = sc.sqrt_dt * SDE_STAGE(j);
 #else
