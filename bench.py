@@ -170,7 +170,6 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import stochastic_b200 as pychastic
-    import stochastic_b200.numpy as jnp
     from stochastic_b200 import runtime, workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -15,7 +15,6 @@ Coefficient tensors come either from `oracle.taylor_ito` (autodiff of torch call
 faithful path) or from a problem's hand-derived numpy closed forms (`coeffs_numpy`, used
 for large CPU-baseline runs and cross-checked against autodiff in the tests).
 """
-import math
 
 import numpy as np
 import torch

@@ -13,7 +13,6 @@ function falls through to numpy on the host, so post-processing code written for
 reference keeps working.
 """
 import builtins
-import math
 
 import numpy as _np
 

@@ -16,7 +16,6 @@ t=0) and error behaviour.  What changes is everything underneath:
 Host-side integer/float arithmetic follows the reference exactly (`int(tmax/dt)`, the chunk
 round-up that overshoots tmax, dt**1.5 in Python double).
 """
-import os
 import ctypes
 from functools import wraps
 from typing import NamedTuple
