@@ -443,6 +443,7 @@ class SDESolver:
             "// generated by stochastic_b200.sde_solver (bead-chain functor)",
             f"#define SDE_NB {nb}", f"#define SDE_F64 {1 if f64 else 0}",
             f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {block}",
+            f"#define SDE_BEAD_DMMA {1 if f64 else 0}",       # fp64: trailing update on the FP64 tensor cores
             '#include "sde_bead_kernel.cuh"', ""])
         prog = runtime.load_program(source, "sde_bead_kernel")
         torch = runtime.require_cuda()
@@ -467,7 +468,7 @@ class SDESolver:
             out_t=out_t.data_ptr(), out_x=out_x.data_ptr(), out_w=out_w.data_ptr())
         elem = 8 if f64 else 4
         npad = -(-d // 8) * 8                      # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh
-        lsize = 17 * ((npad // 8) * npad - 4 * (npad // 8) * (npad // 8 - 1)) // 2
+        lsize = 17 * ((npad // 8) * npad - 4 * (npad // 8) * (npad // 8 - 1)) // 2 + 2
         smem = (7 * d + 8 + lsize) * elem
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         ctas_per_sm = max(1, min(8, (220 * 1024) // (smem + 1024)))
