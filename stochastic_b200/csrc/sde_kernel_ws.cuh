@@ -4,8 +4,8 @@
 // Same entry point, arguments and results as sde_kernel.cuh.  The CTA is split into
 //   * one CONSUMER warpgroup (128 threads = 128 trajectories): keeps (t, x, w) in registers, turns the staged
 //     normals of a step into iterated integrals (WienerGen::wp_assemble) and applies the emitted sde_step;
-//   * two PRODUCER warpgroups (256 threads): nothing but threefry2x32 + erf_inv, writing the normals of the
-//     next step into a two-stage shared-memory ring.
+//   * SDE_WS_PGROUPS PRODUCER warpgroups (3 x 128 threads by default): nothing but threefry2x32 + erf_inv,
+//     writing the normals of the next step into a two-stage shared-memory ring.
 // The roles need very different register files, so the producers shrink theirs and the consumers grow theirs
 // with `setmaxnreg` (Hopper/Blackwell register re-allocation between warpgroups); the hand-off uses named
 // barriers (full[stage]: producers arrive, consumers wait; empty[stage]: the reverse).  The integer-heavy RNG
