@@ -79,3 +79,22 @@ def test_stage_count_formula():
     assert runtime.stage_count(12, 10, "euler") == 12 and runtime.stage_count(2, 10, "milstein") == 0
     assert runtime.pick_block(2, 10, "wagner_platen", True) == 256
     assert runtime.pick_block(6, 10, "wagner_platen", True) * runtime.stage_count(6, 10, "wagner_platen") * 8 <= 200 * 1024
+
+
+def test_plain_c_client_builds_against_the_header_and_compiles_a_kernel(tmp_path):
+    """examples/cabi_client.c: the boundary used from C with no Python in the process.  Here (no GPU) it must link
+    against libsdeb200.so, report the bound NVRTC and NVRTC-compile its hand-written step function for sm_100a."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc / CUDA runtime headers not available")
+    runtime.lib()                                  # fails loudly if the library has not been built
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.join(ROOT, "stochastic_b200")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", os.path.join(ROOT, "examples", "cabi_client.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", "-L" + libdir, "-lsdeb200",
+                           "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe, os.path.join(libdir, "csrc"), "4096"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "sdeb200 ABI 1" in out.stdout and "compiled sde_solve_kernel for sm_100a" in out.stdout
+    assert ("no CUDA device" in out.stdout) or ("E[x_T]" in out.stdout)
