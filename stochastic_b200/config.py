@@ -11,6 +11,10 @@ _STATE = {
     # Wagner-Platen with several noise terms: use the producer/consumer kernel (csrc/sde_kernel_ws.cuh) whenever
     # its two-stage ring of staged normals fits in shared memory.  False forces the single-role kernel.
     "warp_specialize": True,
+    # Emitter: a denominator that divides two or more expressions of a step function is inverted once and the
+    # divisions become multiplications (an FP64 division costs ~12 instructions on the GPU).  Changes the last bit of
+    # those quotients, so it is opt-in: the default keeps the operations the user's functions spell out.
+    "reciprocal_division": False,
 }
 
 

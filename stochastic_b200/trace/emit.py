@@ -34,12 +34,23 @@ def _literal(v, f64):
     return s if f64 else s + "f"
 
 
-def emit_body(outputs, var_names, f64=True, lang="cuda", indent="    "):
+def emit_body(outputs, var_names, f64=True, lang="cuda", indent="    ", reciprocal_division=None):
     """outputs: list of (lhs_text, Expr).  Returns the statement list as text.
 
-    All temporaries are computed before any output is assigned, so outputs may alias inputs."""
+    All temporaries are computed before any output is assigned, so outputs may alias inputs.
+    reciprocal_division (default: config "reciprocal_division"): denominators shared by two or more divisions are
+    inverted once and multiplied with."""
+    if reciprocal_division is None:
+        from .. import config
+        reciprocal_division = config.get("reciprocal_division")
     roots = [e for _, e in outputs]
     order = E.topo_order(roots)
+    den_uses = {}
+    if reciprocal_division:
+        for n in order:
+            if n.op == "div" and n.args[1].op != "const":
+                den_uses[n.args[1].id] = den_uses.get(n.args[1].id, 0) + 1
+    recip = {}                                   # denominator id -> name of its reciprocal
     # sin/cos of the same argument -> one sincos call
     sin_of, cos_of = {}, {}
     for n in order:
@@ -84,7 +95,17 @@ def emit_body(outputs, var_names, f64=True, lang="cuda", indent="    "):
         elif op == "mul":
             rhs = f"{a[0]} * {a[1]}"
         elif op == "div":
-            rhs = f"{a[0]} / {a[1]}"
+            den = n.args[1]
+            if den_uses.get(den.id, 0) >= 2:
+                if den.id not in recip:
+                    recip[den.id] = f"r{len(recip)}"
+                    lines.append(f"const real {recip[den.id]} = (real)1 / {a[1]};")
+                if n.args[0].op == "const" and n.args[0].value == 1.0:
+                    name[n.id] = recip[den.id]   # 1 / den is the reciprocal itself
+                    continue
+                rhs = f"{a[0]} * {recip[den.id]}"
+            else:
+                rhs = f"{a[0]} / {a[1]}"
         elif op == "neg":
             rhs = f"-{a[0]}"
         elif op == "sign":

@@ -128,3 +128,39 @@ def test_emitted_c_matches_interpreter_for_a_batch_of_expressions():
         lib.f(x.ctypes.data, out.ctypes.data)
         want = np.array([float(v) for v in E.evaluate(exprs, x)])
         assert np.allclose(out, want, rtol=1e-12, atol=1e-12)
+
+
+def test_reciprocal_division_option_keeps_values_to_the_last_bits():
+    """config "reciprocal_division": shared denominators are inverted once.  Same values up to a couple of ulp, fewer
+    divisions in the text, and the default (off) text is unchanged."""
+    from stochastic_b200 import workloads
+    from stochastic_b200.trace.taylor import TracedProblem, step_expressions
+    prob = workloads.polar_walk(4.0, (2.0, 0.0), f64=True)
+    tp = TracedProblem(prob.a, prob.b, 2)
+    outs, sv = step_expressions(tp, "wagner_platen")
+    names = {i: f"x[{i}]" for i in range(sv.count)}
+    texts = {}
+    libs = {}
+    for flag in (False, True):
+        body = emit.emit_body([(f"out[{i}]", e) for i, e in enumerate(outs)], names, f64=True, lang="c",
+                              reciprocal_division=flag)
+        texts[flag] = body
+        src = ("#define _GNU_SOURCE\n#include <math.h>\n#include <stdbool.h>\ntypedef double real;\n"
+               "void f(const real* x, real* out) {\n" + body + "\n}\n")
+        tmp = tempfile.mkdtemp()
+        c, so = os.path.join(tmp, "f.c"), os.path.join(tmp, "f.so")
+        with open(c, "w") as fh:
+            fh.write(src)
+        subprocess.check_call(["gcc", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, c, "-lm"])
+        libs[flag] = ctypes.CDLL(so)
+        libs[flag].f.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert texts[False].count(" / ") >= 10 and texts[True].count(" / ") <= 3
+    assert emit.emit_body([(f"out[{i}]", e) for i, e in enumerate(outs)], names, f64=True, lang="c") == texts[False]
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        x = np.concatenate([[rng.uniform(0.5, 3.0), rng.uniform(-3, 3)], rng.normal(size=sv.count - 2) * 0.1])
+        x[sv.dt] = 2.0 ** -5
+        o0, o1 = np.zeros(len(outs)), np.zeros(len(outs))
+        libs[False].f(x.ctypes.data, o0.ctypes.data)
+        libs[True].f(x.ctypes.data, o1.ctypes.data)
+        assert np.allclose(o0, o1, rtol=1e-14, atol=1e-15)
