@@ -8,6 +8,8 @@ from stochastic_b200 import workloads
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 296 * 128 * 8
 e = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 scheme = sys.argv[3] if len(sys.argv) > 3 else "wagner_platen"
+if os.environ.get("RECIP"):
+    pychastic.config.update("reciprocal_division", bool(int(os.environ["RECIP"])))
 prob = workloads.polar_walk(4.0, (2.0, 0.0), 1.0, f64=True)
 solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=2.0 ** -e)
 if os.environ.get("BLOCK"):
