@@ -48,7 +48,8 @@ typedef struct sdeb200_solve_args {
     void* out_t;             /* device (traj_count, n_snapshots)      or NULL */
     void* out_x;             /* device (traj_count, n_snapshots, d)   or NULL */
     void* out_w;             /* device (traj_count, n_snapshots, m)   or NULL */
-    double* moments;         /* device (n_obs, 2) sums / sums of squares, accumulated; or NULL */
+    double* moments;         /* device (n_obs, 2) sums / sums of squares, accumulated - (n_snapshots, n_obs, 2) for a
+                                program built with SDE_OBS_SNAP (observables at every snapshot); or NULL */
     void* out_hit;           /* device (traj_count, 2 + d): first-passage flag, time, state (kernels built with an
                                 event function; replaces the host post-processing of examples/hit.py:40-58); or NULL */
 } sdeb200_solve_args_t;

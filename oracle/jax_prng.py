@@ -49,10 +49,14 @@ def threefry2x32(k0, k1, x0, x1):
     return x0, x1
 
 
-def PRNGKey(seed):
-    """`jax.random.PRNGKey(seed)` raw key data: [hi32(seed), lo32(seed)]."""
+def PRNGKey(seed, x64=False):
+    """`jax.random.PRNGKey(seed)` raw key data (jax/_src/prng.py::random_seed + threefry_seed).
+
+    An int seed becomes `jnp.asarray(np.int64(seed))`: int32 (wrapped) unless jax_enable_x64, then
+    k1 = convert(shift_right_logical(seed, 32)) - which is 0 for a 32-bit seed - and k2 = seed & 0xFFFFFFFF.
+    So 32-bit mode gives [0, lo32(seed)] (seed=-1 -> [0, 0xFFFFFFFF]) and 64-bit mode [hi32(seed), lo32(seed)]."""
     seed = int(seed)
-    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=U32)
+    return np.array([((seed >> 32) & 0xFFFFFFFF) if x64 else 0, seed & 0xFFFFFFFF], dtype=U32)
 
 
 def threefry_2x32(key, counts):

@@ -90,7 +90,7 @@ def solve_many(problem, scheme="euler", dt=0.01, n_trajectories=1, seed=0, chunk
     chunk, n_chunks, cpr, n_frag = chunk_arithmetic(problem.tmax, dt, chunk_size, chunks_per_randomization)
     S = chunk * cpr
 
-    keys = jax_prng.split(jax_prng.PRNGKey(seed), n_total, layout)
+    keys = jax_prng.split(jax_prng.PRNGKey(seed, x64=(np.dtype(dtype) == np.float64)), n_total, layout)
     if traj_slice is not None:
         b0, cnt = traj_slice
         keys = keys[b0:b0 + cnt]

@@ -8,12 +8,18 @@
 // Included AFTER sde_core.cuh and after the problem's device functions:
 //   __device__ void sde_step(real (&x)[SDE_D], const sdeb::Integrals& I, real dt);   // required
 //   __device__ void sde_post(real (&x)[SDE_D]);                      // if SDE_HAS_POST
-//   __device__ void sde_observe(const real*, const real*, real, double (&obs)[SDE_NOBS]);  // if SDE_NOBS > 0
+//   __device__ void sde_observe(const real* x, const real* w, real t, const real* x_ref, double (&obs)[SDE_NOBS]);  // if SDE_NOBS > 0
 //   __device__ real sde_event(const real* x, const real* w, real t);                      // if SDE_HAS_EVENT
 #pragma once
 
 #ifndef SDE_NOBS
 #define SDE_NOBS 0
+#endif
+#ifndef SDE_OBS_SNAP
+#define SDE_OBS_SNAP 0    // 1: observables are accumulated at EVERY snapshot into moments[snapshot][k][2]
+#endif
+#ifndef SDE_OBS_REF
+#define SDE_OBS_REF 0     // 1: sde_observe also reads x_ref, the state at the first snapshot
 #endif
 #ifndef SDE_HAS_POST
 #define SDE_HAS_POST 0
@@ -32,6 +38,8 @@
 #ifndef SDE_LOCKSTEP
 #define SDE_LOCKSTEP (SDE_STAGE_COUNT > 0)
 #endif
+
+#include "sde_hooks.cuh"
 
 namespace sdeb {
 
@@ -53,7 +61,7 @@ struct SolveArgs {
     real* out_t;              // (traj_count, n_snapshots)            or nullptr
     real* out_x;              // (traj_count, n_snapshots, SDE_D)     or nullptr
     real* out_w;              // (traj_count, n_snapshots, SDE_M)     or nullptr
-    double* moments;          // (SDE_NOBS, 2): sum, sum of squares   or nullptr
+    double* moments;          // (SDE_NOBS, 2): sum, sum of squares; (n_snapshots, SDE_NOBS, 2) if SDE_OBS_SNAP   or nullptr
     real* out_hit;            // (traj_count, 2 + SDE_D): flag, time, state of the first passage   or nullptr
 };
 
@@ -84,7 +92,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
     // Threads past the end integrate trajectory 0 again (no stores): every thread of the CTA then runs the
     // same number of steps, which the per-step barrier below relies on.
     const u64 tid = active ? tid_raw : 0;
-#if SDE_NOBS > 0
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
     double obs[SDE_NOBS];
 #pragma unroll
     for (int k = 0; k < SDE_NOBS; ++k) obs[k] = 0.0;
@@ -101,6 +109,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
         for (int i = 0; i < SDE_D; ++i) x[i] = A.x0[tid * (u64)A.x0_stride + i];
 #pragma unroll
         for (int j = 0; j < SDE_M; ++j) w[j] = RC(0.0);
+#if SDE_OBS_REF
+        real xref[SDE_D];     // state at the first snapshot (what the reference's MSD post-processing subtracts)
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) xref[i] = x[i];
+#else
+        const real* const xref = x;
+#endif
 
         StepScale sc;
         sc.dt = (real)A.dt;
@@ -161,6 +176,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
                     if (++in_chunk < A.chunk) continue;
                     in_chunk = 0;
                     // ---- snapshot `snap` -----------------------------------------------------------------
+#if SDE_OBS_REF
+                    if (snap == 0) {
+#pragma unroll
+                        for (int i = 0; i < SDE_D; ++i) xref[i] = x[i];
+                    }
+#endif
+#if SDE_NOBS > 0 && SDE_OBS_SNAP
+                    if (A.moments) observe_accumulate_warp(x, w, t, xref, active, A.moments + (u64)snap * (2 * SDE_NOBS));
+#endif
 #if SDE_SNAP_TILE > 1
                 {
                     real* col = snapbuf + tile_fill * SDE_SNAP_PITCH + lane;
@@ -239,11 +263,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
             for (int i = 0; i < SDE_D; ++i) o[2 + i] = hit_x[i];
         }
 #endif
-#if SDE_NOBS > 0
-        sde_observe(x, w, t, obs);
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
+        sde_observe(x, w, t, xref, obs);
 #endif
     }
-#if SDE_NOBS > 0
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
     // block reduction of sum and sum of squares, one atomicAdd pair per observable per block
     __shared__ double red[2 * SDE_NOBS][SDE_BLOCK / 32];
     const int red_lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

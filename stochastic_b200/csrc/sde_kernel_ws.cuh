@@ -19,6 +19,12 @@
 #ifndef SDE_NOBS
 #define SDE_NOBS 0
 #endif
+#ifndef SDE_OBS_SNAP
+#define SDE_OBS_SNAP 0    // 1: observables are accumulated at EVERY snapshot into moments[snapshot][k][2]
+#endif
+#ifndef SDE_OBS_REF
+#define SDE_OBS_REF 0     // 1: sde_observe also reads x_ref, the state at the first snapshot
+#endif
 #ifndef SDE_HAS_POST
 #define SDE_HAS_POST 0
 #endif
@@ -45,6 +51,8 @@
 static_assert(SDE_BLOCK == SDE_WS_NC + SDE_WS_NP, "SDE_BLOCK must be 128 consumers + 128 per producer warpgroup");
 static_assert(SDE_STAGE_STRIDE == SDE_WS_NC, "staging rows hold one value per consumer");
 static_assert(SDE_STAGE_COUNT > 0, "warp specialisation is for staged generators");
+
+#include "sde_hooks.cuh"
 
 namespace sdeb {
 
@@ -185,7 +193,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 
     // ==================================== consumers =====================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(SDE_WS_CONSUMER_REGS));
-#if SDE_NOBS > 0
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
     double obs[SDE_NOBS];
 #pragma unroll
     for (int k = 0; k < SDE_NOBS; ++k) obs[k] = 0.0;
@@ -197,6 +205,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
         for (int i = 0; i < SDE_D; ++i) x[i] = A.x0[tid * (u64)A.x0_stride + i];
 #pragma unroll
         for (int j = 0; j < SDE_M; ++j) w[j] = RC(0.0);
+#if SDE_OBS_REF
+        real xref[SDE_D];     // state at the first snapshot
+#pragma unroll
+        for (int i = 0; i < SDE_D; ++i) xref[i] = x[i];
+#else
+        const real* const xref = x;
+#endif
         StepScale sc;
         sc.dt = (real)A.dt;
         sc.sqrt_dt = sqrt((real)A.dt);
@@ -276,6 +291,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 #endif
             if (++in_chunk < A.chunk) continue;
             in_chunk = 0;
+#if SDE_OBS_REF
+            if (snap == 0) {
+#pragma unroll
+                for (int i = 0; i < SDE_D; ++i) xref[i] = x[i];
+            }
+#endif
+#if SDE_NOBS > 0 && SDE_OBS_SNAP
+            if (A.moments) observe_accumulate_warp(x, w, t, xref, active, A.moments + (u64)snap * (2 * SDE_NOBS));
+#endif
             if (active) {
                 const u64 row = tid * (u64)A.n_snapshots + snap;
                 if (A.out_t) A.out_t[row] = t;
@@ -299,11 +323,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             for (int i = 0; i < SDE_D; ++i) o[2 + i] = hit_x[i];
         }
 #endif
-#if SDE_NOBS > 0
-        sde_observe(x, w, t, obs);
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
+        sde_observe(x, w, t, xref, obs);
 #endif
     }
-#if SDE_NOBS > 0
+#if SDE_NOBS > 0 && !SDE_OBS_SNAP
     __shared__ double red[2 * SDE_NOBS][SDE_WS_NC / 32];
     const int red_lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll

@@ -23,9 +23,18 @@ def threefry2x32(key, x0, x1):
     return x0, x1
 
 
-def PRNGKey(seed):
+def PRNGKey(seed, x64=None):
+    """Raw key data of `jax.random.PRNGKey(seed)`.
+
+    JAX converts an integer seed to the default integer type first: int32 unless `jax_enable_x64` is set.  The high
+    key word is therefore 0 in 32-bit mode (the seed wraps: -1 -> [0, 0xFFFFFFFF], 2**33 + 5 -> [0, 5]) and
+    `(seed >> 32) & 0xFFFFFFFF` in 64-bit mode (-1 -> [0xFFFFFFFF, 0xFFFFFFFF]).  `x64=None` reads the package
+    switch `config "enable_x64"`; the solver passes True for double-precision runs."""
+    if x64 is None:
+        from . import config
+        x64 = config.get("enable_x64")
     seed = int(seed)
-    return (seed >> 32) & _M, seed & _M
+    return ((seed >> 32) & _M) if x64 else 0, seed & _M
 
 
 def fold_in(key, data):

@@ -185,7 +185,8 @@ def nvrtc_version():
 def _core_fingerprint():
     h = hashlib.sha256()
     h.update("nvrtc %d.%d\n".encode() % nvrtc_version()[:2])      # cubins of different compilers never mix
-    for name in ("sde_core.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh", "sde_bead_kernel.cuh"):
+    for name in ("sde_core.cuh", "sde_hooks.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh",
+                 "sde_bead_kernel.cuh"):
         with open(os.path.join(CSRC_DIR, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()

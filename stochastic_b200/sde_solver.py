@@ -17,12 +17,14 @@ Host-side integer/float arithmetic follows the reference exactly (`int(tmax/dt)`
 round-up that overshoots tmax, dt**1.5 in Python double).
 """
 import ctypes
+import os
+from collections import OrderedDict
 from functools import wraps
 from typing import NamedTuple
 
 import numpy as np
 
-from . import config, jnp, runtime
+from . import config, jnp, prng, runtime
 from .autodiff import hessian, jacobian
 from .device_array import DeviceArray
 from .sde_problem import SDEProblem
@@ -92,13 +94,13 @@ def chunk_arithmetic(tmax, dt, chunk_size, chunks_per_randomization):
     return chunk_size, number_of_chunks, chunks_per_randomization, number_of_chunks // chunks_per_randomization
 
 
-def prng_key(seed):
-    """Raw key data of jax.random.PRNGKey(seed); a (hi, lo) pair of uint32 words is passed through unchanged,
-    so that a key derived on the host (e.g. `prng.fold_in(PRNGKey(seed), rank)`) can be used as `seed`."""
+def prng_key(seed, x64=None):
+    """Raw key data of jax.random.PRNGKey(seed) (`prng.PRNGKey`: the high word is 0 unless the run is in 64-bit
+    mode, as in JAX); a (hi, lo) pair of uint32 words is passed through unchanged, so that a key derived on the
+    host (e.g. `prng.fold_in(PRNGKey(seed), rank)`) can be used as `seed`."""
     if isinstance(seed, (tuple, list, np.ndarray)) and len(seed) == 2:
         return int(seed[0]) & 0xFFFFFFFF, int(seed[1]) & 0xFFFFFFFF
-    seed = int(seed)
-    return (seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF
+    return prng.PRNGKey(seed, x64)
 
 
 def _c_function(name, signature, outputs, var_names, f64):
@@ -115,17 +117,37 @@ def _emit_post(post, d, f64):
     return _c_function("sde_post", "real (&x)[SDE_D]", [(f"x[{i}]", E.wrap(v)) for i, v in enumerate(y)], names, f64), d
 
 
+def observe_arity(observe):
+    """3: observables(x, w, t); 4: observables(x, w, t, x_ref) with x_ref = the state at the first snapshot."""
+    import inspect
+    try:
+        params = [p for p in inspect.signature(observe).parameters.values()
+                  if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) and p.default is p.empty]
+    except (TypeError, ValueError):
+        return 3
+    if len(params) not in (3, 4):
+        raise ValueError("observables must take (x, w, t) or (x, w, t, x_ref)")
+    return len(params)
+
+
 def _emit_observe(observe, d, m, f64):
     x = jnp.symbols((d,))
     w = jnp.symbols((m,), start=d)
     t = E.var(d + m)
-    o = np.atleast_1d(np.asarray(jnp._as_obj(observe(x, w, t)), dtype=object)).ravel()
+    uses_ref = observe_arity(observe) == 4
+    if uses_ref:
+        xr = jnp.symbols((d,), start=d + m + 1)
+        o = observe(x, w, t, xr)
+    else:
+        o = observe(x, w, t)
+    o = np.atleast_1d(np.asarray(jnp._as_obj(o), dtype=object)).ravel()
     names = {i: f"x[{i}]" for i in range(d)}
     names.update({d + j: f"w[{j}]" for j in range(m)})
     names[d + m] = "t"
-    src = _c_function("sde_observe", "const real* x, const real* w, const real t, double (&obs)[SDE_NOBS]",
-                      [(f"obs[{k}]", E.wrap(v)) for k, v in enumerate(o)], names, f64)
-    return src, o.size
+    names.update({d + m + 1 + i: f"xr[{i}]" for i in range(d)})
+    src = _c_function("sde_observe", "const real* x, const real* w, const real t, const real* xr, "
+                      "double (&obs)[SDE_NOBS]", [(f"obs[{k}]", E.wrap(v)) for k, v in enumerate(o)], names, f64)
+    return src, o.size, uses_ref
 
 
 def _emit_event(event, d, m, f64):
@@ -143,9 +165,31 @@ def _emit_event(event, d, m, f64):
             f"    real ev;\n{body}\n    return ev;\n}}\n")
 
 
+def _emit_hooks(parts, d, m, f64, post, observe, event, observe_at):
+    """Optional device functions of a stepping kernel (sde_post / sde_observe / sde_event) and their macros."""
+    n_obs = 0
+    post_src = obs_src = ev_src = ""
+    if post is not None:
+        post_src, _ = _emit_post(post, d, f64)
+        parts.append("#define SDE_HAS_POST 1")
+    if observe is not None:
+        obs_src, n_obs, uses_ref = _emit_observe(observe, d, m, f64)
+        parts.append(f"#define SDE_NOBS {n_obs}")
+        if observe_at == "snapshots":
+            parts.append("#define SDE_OBS_SNAP 1")
+        elif observe_at != "final":
+            raise ValueError(f"observe_at must be 'final' or 'snapshots', not {observe_at!r}")
+        if uses_ref:
+            parts.append("#define SDE_OBS_REF 1")
+    if event is not None:
+        ev_src = _emit_event(event, d, m, f64)
+        parts.append("#define SDE_HAS_EVENT 1")
+    return n_obs, [post_src, obs_src, ev_src]
+
+
 def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observe=None, p=10, block=None,
                  min_blocks=None, lockstep=None, n_snapshots=1, snap_tile=None, warp_specialize=None, ws_tuning=None,
-                 event=None):
+                 event=None, observe_at="final"):
     """Trace the problem and emit the complete translation unit of its stepping kernel.
 
     Returns a `KernelSource`."""
@@ -158,8 +202,10 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     if warp_specialize is None:
         warp_specialize = config.get("warp_specialize")
     ws = bool(warp_specialize) and scheme == "wagner_platen" and m > 1 and 2 * stage * 128 * elem <= 110 * 1024
+    step_src = lambda: _c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
+                                   [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64)
     if ws:
-        # warp-specialised kernel (csrc/sde_kernel_ws.cuh): 128 consumer + 256 producer threads, two-stage ring
+        # warp-specialised kernel (csrc/sde_kernel_ws.cuh): 128 consumer + 384 producer threads, two-stage ring
         parts = [
             "// generated by stochastic_b200.sde_solver.build_source (warp-specialised)",
             f"#define SDE_D {d}", f"#define SDE_M {m}", f"#define SDE_SCHEME {SCHEME_ID[scheme]}",
@@ -188,24 +234,14 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
                 raise ValueError("SDE_WS_CTAIL must be in [0, 3m] and needs SDE_WS_GROUP == 1")
             # ptxas 12.9 crashes on a call to the out-of-line erf_inv tail from the register-grown consumer branch
             parts.append("#define SDE_TAIL_ATTR __forceinline__")
-        n_obs = 0
-        post_src = obs_src = ""
-        if post is not None:
-            post_src, _ = _emit_post(post, d, f64)
-            parts.append("#define SDE_HAS_POST 1")
-        if observe is not None:
-            obs_src, n_obs = _emit_observe(observe, d, m, f64)
-            parts.append(f"#define SDE_NOBS {n_obs}")
-        ev_src = ""
-        if event is not None:
-            ev_src = _emit_event(event, d, m, f64)
-            parts.append("#define SDE_HAS_EVENT 1")
+        ring_bytes = 2 * stage * 128 * elem
+        n_obs, hooks = _emit_hooks(parts, d, m, f64, post, observe, event, observe_at)
         parts.append('#include "sde_core.cuh"')
         parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
-        parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
-                                 [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
-        parts += [post_src, obs_src, ev_src, '#include "sde_kernel_ws.cuh"']
-        return KernelSource("\n".join(parts) + "\n", m, n_obs, ws_block, 2 * stage * 128 * elem, 128)
+        parts.append(step_src())
+        parts += hooks + ['#include "sde_kernel_ws.cuh"']
+        return KernelSource("\n".join(parts) + "\n", m, n_obs, ws_block,
+                            ring_bytes, 128)
     block = runtime.pick_block(m, p, scheme, f64, block)
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
@@ -232,28 +268,66 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         parts.append(f"#define SDE_MIN_BLOCKS {int(min_blocks)}")
     if lockstep is not None:
         parts.append(f"#define SDE_LOCKSTEP {1 if lockstep else 0}")
-    n_obs = 0
-    post_src = obs_src = ""
-    if post is not None:
-        post_src, _ = _emit_post(post, d, f64)
-        parts.append("#define SDE_HAS_POST 1")
-    if observe is not None:
-        obs_src, n_obs = _emit_observe(observe, d, m, f64)
-        parts.append(f"#define SDE_NOBS {n_obs}")
-    ev_src = ""
-    if event is not None:
-        ev_src = _emit_event(event, d, m, f64)
-        parts.append("#define SDE_HAS_EVENT 1")
+    n_obs, hooks = _emit_hooks(parts, d, m, f64, post, observe, event, observe_at)
     parts.append('#include "sde_core.cuh"')
     parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
-    parts.append(_c_function("sde_step", "real (&x)[SDE_D], const sdeb::Integrals& I, const real dt",
-                             [(f"x[{i}]", e) for i, e in enumerate(outs)], sv.names, f64))
-    parts.append(post_src)
-    parts.append(obs_src)
-    parts.append(ev_src)
+    parts.append(step_src())
+    parts += hooks
     parts.append('#include "sde_kernel.cuh"')
     return KernelSource("\n".join(parts) + "\n", m, n_obs, block,
                         stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile), block)
+
+
+def bead_ring_source(n_beads, f64, layout, block, twist=False):
+    """Translation unit of the CTA-per-trajectory bead-chain kernel (csrc/sde_bead_kernel.cuh)."""
+    return "\n".join([
+        "// generated by stochastic_b200.sde_solver (bead-chain functor)",
+        f"#define SDE_NB {n_beads}", f"#define SDE_F64 {1 if f64 else 0}",
+        f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {block}",
+        f"#define SDE_BEAD_DMMA {1 if f64 else 0}",       # fp64: trailing update on the FP64 tensor cores
+        f"#define SDE_BEAD_TWIST {1 if twist else 0}",    # writhe-dependent twist energy (reference :57)
+        '#include "sde_bead_kernel.cuh"', ""])
+
+
+class _Plan:
+    """One compiled-kernel choice of `SDESolver`: the emitted source and its launch geometry, plus the loaded
+    program per device.  Cached per (callables, scheme, dtype, knobs), so that a repeated `solve_many` on the same
+    problem neither traces, differentiates, emits nor hashes anything again."""
+    __slots__ = ("ks", "entry", "programs", "keepalive")
+
+    def __init__(self, ks, entry, keepalive):
+        self.ks, self.entry, self.programs, self.keepalive = ks, entry, {}, keepalive
+
+    def program(self):
+        """The kernel loaded on the current device (raises without a CUDA device)."""
+        if os.environ.get("SDEB200_PRECOMPILE_ONLY"):
+            return runtime.load_program(self.ks.source, self.entry)
+        torch = runtime.require_cuda()
+        dev = torch.cuda.current_device()
+        prog = self.programs.get(dev)
+        if prog is None:
+            prog = self.programs[dev] = runtime.load_program(self.ks.source, self.entry)
+        return prog
+
+
+_PLANS = OrderedDict()
+_PLAN_LIMIT = 256
+PLAN_STATS = {"hits": 0, "misses": 0}
+
+
+def _cached_plan(key, keepalive, make):
+    plan = _PLANS.get(key)
+    if plan is not None:
+        _PLANS.move_to_end(key)
+        PLAN_STATS["hits"] += 1
+        return plan
+    PLAN_STATS["misses"] += 1
+    ks, entry = make()
+    # the key holds ids of the user's callables: keep them alive as long as the entry, so an id is never reused
+    plan = _PLANS[key] = _Plan(ks, entry, keepalive)
+    while len(_PLANS) > _PLAN_LIMIT:
+        _PLANS.popitem(last=False)
+    return plan
 
 
 class SDESolver:
@@ -285,28 +359,77 @@ class SDESolver:
         self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
 
-    def compile(self, problem, step_post_processing=None, observables=None, prng_layout=None):
-        """Trace `problem`, emit its kernel and NVRTC-compile it into the cubin cache (no GPU needed)."""
+    # -- kernel selection (shared by compile and solve_many) -----------------------------------
+    def _knobs(self):
+        return (self.block_size, self.min_blocks_per_sm, self.lockstep, self.snap_tile, self.warp_specialize,
+                tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel,
+                config.get("warp_specialize"), config.get("reciprocal_division"))
+
+    @staticmethod
+    def _uses_bead_kernel(problem, force):
+        return getattr(problem, "bead_ring", None) is not None and (problem.dimension > 24 or force)
+
+    def _bead_plan(self, problem, f64, layout):
+        par = problem.bead_ring
+        nb = par["n_beads"]
+        block = max(128, -(-3 * nb // 32) * 32)
+        if self.block_size:
+            if self.block_size % 32 or not block <= self.block_size <= 1024:
+                raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
+            block = int(self.block_size)
+        twist = bool(par.get("twist"))
+        key = ("bead", nb, f64, layout, block, twist)
+        return _cached_plan(key, (), lambda: (KernelSource(bead_ring_source(nb, f64, layout, block, twist), 3 * nb, 0,
+                                                           block, 0, 1), "sde_bead_kernel"))
+
+    def _plan(self, problem, d, f64, layout, post, observe, event, n_snapshots, observe_at, first_sight=None):
+        """The (cached) stepping kernel for this problem and these options; `first_sight()` runs before the problem
+        is traced for the first time."""
+        snap_class = min(int(n_snapshots), 16)             # all that pick_snap_tile reads of the snapshot count
+        key = ("step", id(problem.a), id(problem.b), d, self.scheme, f64, layout, id(post) if post else None,
+               id(observe) if observe else None, id(event) if event else None, observe_at, snap_class, self._knobs())
+        return _cached_plan(key, (problem.a, problem.b, post, observe, event), lambda: (
+            first_sight and first_sight(),
+            build_source(problem.a, problem.b, d, self.scheme, f64, layout, post=post, observe=observe,
+                         block=self.block_size, min_blocks=self.min_blocks_per_sm, lockstep=self.lockstep,
+                         n_snapshots=n_snapshots, snap_tile=self.snap_tile, warp_specialize=self.warp_specialize,
+                         ws_tuning=self.ws_tuning, event=event, observe_at=observe_at), "sde_solve_kernel")[1:])
+
+    def compile(self, problem, step_post_processing=None, observables=None, prng_layout=None, chunk_size=1,
+                chunks_per_randomization=None, max_snapshots=None, first_passage=None, store_trajectories=True,
+                observe_at="final"):
+        """Trace `problem`, emit the kernel that `solve_many` would launch with the same keyword arguments and
+        NVRTC-compile it into the cubin cache (no GPU needed).  Returns the cache key."""
+        if self.scheme not in SCHEMES:
+            raise ValueError(f"unknown scheme {self.scheme!r}; expected one of {SCHEMES}")
         x0 = np.asarray(jnp._host(problem.x0))
         f64 = x0.dtype == np.float64
         d = x0.shape[-1]
         layout = prng_layout or config.get("prng_layout")
-        source = build_source(problem.a, problem.b, d, self.scheme, f64, layout, post=step_post_processing,
-                              observe=observables, block=self.block_size, min_blocks=self.min_blocks_per_sm,
-                              lockstep=self.lockstep, warp_specialize=self.warp_specialize,
-                              ws_tuning=self.ws_tuning)[0]
-        return runtime.compile_source(source)[0]
+        if self._uses_bead_kernel(problem, self.use_bead_kernel):
+            plan = self._bead_plan(problem, f64, layout)
+        else:
+            _, n_chunks, _, _ = chunk_arithmetic(problem.tmax, self.dt, chunk_size, chunks_per_randomization)
+            n_snap = n_chunks if max_snapshots is None else min(n_chunks, int(max_snapshots))
+            plan = self._plan(problem, d, f64, layout, step_post_processing, observables, first_passage,
+                              n_snap if store_trajectories else 1, observe_at)
+        return runtime.compile_source(plan.ks.source)[0]
 
     # -- the hot path ------------------------------------------------------------------------
     def solve_many(self, problem: SDEProblem, n_trajectories=1, step_post_processing=None, seed=0, chunk_size=1,
                    chunks_per_randomization=None, progress_bar=True, *, observables=None, first_passage=None,
-                   store_trajectories=True, traj_range=None, max_snapshots=None, prng_layout=None):
+                   store_trajectories=True, traj_range=None, max_snapshots=None, prng_layout=None,
+                   observe_at="final"):
         """Integrate `n_trajectories` sample paths (reference `sde_solver.py:82-304`).
 
         Extensions (keyword-only, not in the reference):
-        observables        callable (x, w, t) -> vector; its per-trajectory values at the final time are
-                           reduced on the device to sums / sums of squares (result key 'moments', shape
-                           (n_obs, 2), plus 'count').
+        observables        callable (x, w, t) -> vector, or (x, w, t, x_ref) -> vector with x_ref the state at the
+                           first snapshot (what the reference's mean-square-displacement post-processing subtracts,
+                           `examples/jfm.py:134-171`); its per-trajectory values are reduced on the device to sums /
+                           sums of squares (result key 'moments', plus 'count').
+        observe_at         'final' (default): observables are evaluated once, at the last snapshot; 'moments' has
+                           shape (n_obs, 2).  'snapshots': at every snapshot; shape (n_snapshots, n_obs, 2) - the
+                           ensemble statistics of a published study without ever storing (n_traj, n_snap, d).
         first_passage      callable (x, w, t) -> scalar event function; for every trajectory the first step after which
                            it is positive is located by linear interpolation between the states before and after
                            that step, on the device (result keys 'hit_flag', 'hit_time', 'hit_state'; the host
@@ -320,7 +443,7 @@ class SDESolver:
         scheme = self.scheme
         if scheme not in SCHEMES:
             raise ValueError(f"unknown scheme {scheme!r}; expected one of {SCHEMES}")
-        if getattr(problem, "bead_ring", None) is not None and (problem.dimension > 24 or self.use_bead_kernel):
+        if self._uses_bead_kernel(problem, self.use_bead_kernel):
             if step_post_processing is not None or observables is not None or first_passage is not None:
                 raise NotImplementedError("the bead-chain kernel supports neither step_post_processing, observables "
                                           "nor first_passage")
@@ -339,23 +462,20 @@ class SDESolver:
         n_total = ics.shape[0] if multiple_ic else int(n_trajectories)
         d = ics.shape[1]
 
-        a0 = np.shape(jnp._as_obj(problem.a(ics[0])))
-        b0 = np.shape(jnp._as_obj(problem.b(ics[0])))
-        assert ics[0].shape == a0
-        assert ics[0].shape[0] == b0[0]
-
         layout = prng_layout or config.get("prng_layout")
         chunk, n_chunks, cpr, n_frag = chunk_arithmetic(problem.tmax, self.dt, chunk_size, chunks_per_randomization)
         n_snap = n_chunks if max_snapshots is None else min(n_chunks, int(max_snapshots))
-        source, m, n_obs, block, dyn_smem, traj_per_block = build_source(problem.a, problem.b, d, scheme, f64, layout,
-                                                         post=step_post_processing, observe=observables,
-                                                         block=self.block_size, min_blocks=self.min_blocks_per_sm,
-                                                         lockstep=self.lockstep,
-                                                         n_snapshots=(n_snap if store_trajectories else 1),
-                                                         snap_tile=self.snap_tile,
-                                                         warp_specialize=self.warp_specialize,
-                                                         ws_tuning=self.ws_tuning, event=first_passage)
-        prog = runtime.load_program(source, "sde_solve_kernel")   # raises without a CUDA device
+
+        def shape_assertions():      # the reference's (`sde_solver.py:151-152`), once per set of callables
+            a0 = np.shape(jnp._as_obj(problem.a(ics[0])))
+            b0 = np.shape(jnp._as_obj(problem.b(ics[0])))
+            assert ics[0].shape == a0
+            assert ics[0].shape[0] == b0[0]
+
+        plan = self._plan(problem, d, f64, layout, step_post_processing, observables, first_passage,
+                          n_snap if store_trajectories else 1, observe_at, first_sight=shape_assertions)
+        source, m, n_obs, block, dyn_smem, traj_per_block = plan.ks
+        prog = plan.program()   # raises without a CUDA device
         torch = runtime.require_cuda()
 
         S = chunk * cpr
@@ -379,10 +499,13 @@ class SDESolver:
             out_t = torch.empty((count, n_snap), dtype=tdt, device=dev)
             out_x = torch.empty((count, n_snap, d), dtype=tdt, device=dev)
             out_w = torch.empty((count, n_snap, m), dtype=tdt, device=dev)
-        moments = torch.zeros((n_obs, 2), dtype=torch.float64, device=dev) if n_obs else None
+        moments = None
+        if n_obs:
+            shape = (n_snap, n_obs, 2) if observe_at == "snapshots" else (n_obs, 2)
+            moments = torch.zeros(shape, dtype=torch.float64, device=dev)
         out_hit = torch.empty((count, 2 + d), dtype=tdt, device=dev) if first_passage is not None else None
 
-        ka, kb = prng_key(seed)
+        ka, kb = prng_key(seed, x64=f64 or config.get("enable_x64"))
         args = runtime.SolveArgs(
             key_a=ka, key_b=kb, n_fragments=n_frag, cpr=cpr, chunk=chunk, n_snapshots=n_snap,
             n_traj_total=n_total, traj_begin=begin, traj_count=count,
@@ -434,18 +557,9 @@ class SDESolver:
         nb = par["n_beads"]
         d = 3 * nb
         layout = prng_layout or config.get("prng_layout")
-        block = max(128, -(-d // 32) * 32)
-        if self.block_size:
-            if self.block_size % 32 or not block <= self.block_size <= 1024:
-                raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
-            block = int(self.block_size)
-        source = "\n".join([
-            "// generated by stochastic_b200.sde_solver (bead-chain functor)",
-            f"#define SDE_NB {nb}", f"#define SDE_F64 {1 if f64 else 0}",
-            f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {block}",
-            f"#define SDE_BEAD_DMMA {1 if f64 else 0}",       # fp64: trailing update on the FP64 tensor cores
-            '#include "sde_bead_kernel.cuh"', ""])
-        prog = runtime.load_program(source, "sde_bead_kernel")
+        plan = self._bead_plan(problem, f64, layout)
+        block = plan.ks.block
+        prog = plan.program()
         torch = runtime.require_cuda()
         chunk, n_chunks, cpr, n_frag = chunk_arithmetic(problem.tmax, self.dt, chunk_size, chunks_per_randomization)
         n_snap = n_chunks if max_snapshots is None else min(n_chunks, int(max_snapshots))
@@ -459,7 +573,7 @@ class SDESolver:
         out_t = torch.empty((count, n_snap), dtype=tdt, device=dev)
         out_x = torch.empty((count, n_snap, d), dtype=tdt, device=dev)
         out_w = torch.empty((count, n_snap, d), dtype=tdt, device=dev)
-        ka, kb = prng_key(seed)
+        ka, kb = prng_key(seed, x64=f64 or config.get("enable_x64"))
         args = runtime.BeadArgs(
             key_a=ka, key_b=kb, n_fragments=n_frag, cpr=cpr, chunk=chunk, n_snapshots=n_snap, n_traj_total=n_total,
             traj_begin=begin, traj_count=count, x0=x0_dev.data_ptr(), x0_stride=(d if multiple_ic else 0),

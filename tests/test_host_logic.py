@@ -200,6 +200,42 @@ def test_generated_source_is_deterministic_and_cached_by_content():
     assert s1 == s2 and "sincos" in s1 and "#define SDE_SCHEME 2" in s1
 
 
+_EMIT_SCRIPT = """
+import hashlib, sys
+sys.path.insert(0, {root!r})
+from stochastic_b200 import workloads
+from stochastic_b200.sde_solver import build_source
+def src(name):
+    if name == "garch":
+        p = workloads.garch(f64=True)
+        return build_source(p.a, p.b, 2, "milstein", True, "original").source
+    if name == "polar":
+        p = workloads.polar_walk(4.0, (2.0, 0.0), f64=True)
+        return build_source(p.a, p.b, 2, "wagner_platen", True, "original", observe=workloads.polar_error_observables()).source
+    if name == "beads":
+        p = workloads.four_beads(f64=True)
+        return build_source(p.a, p.b, 12, "euler", True, "original").source
+    p, post = workloads.brownian_rotations(f64=True)
+    return build_source(p.a, p.b, 3, "euler", True, "original", post=post).source
+for name in sys.argv[1:]:
+    print(name, hashlib.sha256(src(name).encode()).hexdigest())
+"""
+
+
+def test_emitted_source_does_not_depend_on_trace_history(tmp_path):
+    """The CUDA text of a problem (hence its cubin-cache key and its FMA contraction) must be a pure function of the
+    problem: commutative operands are ordered by a structural key, not by the order in which a process happened to
+    create the nodes, and not by Python's per-process string hashing."""
+    script = tmp_path / "emit.py"
+    script.write_text(_EMIT_SCRIPT.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    runs = []
+    for seed, order in (("0", ["garch", "polar", "beads", "rot"]), ("7", ["rot", "beads", "polar", "garch", "polar"])):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        out = subprocess.run([os.sys.executable, str(script)] + order, env=env, check=True, capture_output=True, text=True)
+        runs.append(dict(line.split() for line in out.stdout.strip().splitlines()))
+    assert runs[0] == runs[1] and len(runs[0]) == 4
+
+
 # -- tracer details ----------------------------------------------------------------------------------
 def test_grad_composes_inside_traced_functions():
     u = lambda x: jnp.sum(x ** 2) * jnp.sin(x[0])
@@ -312,10 +348,21 @@ def test_host_prng_matches_oracle():
     assert prng.fold_in(prng.PRNGKey(0), 1) == (928981903, 3453687069)
     for seed, n in [(0, 5), (7, 1), (123456789012, 4)]:
         for layout in ("original", "partitionable"):
-            assert prng.split(prng.PRNGKey(seed), n, layout) == [tuple(int(v) for v in k) for k in
-                                                                 jax_prng.split(jax_prng.PRNGKey(seed), n, layout)]
+            for x64 in (False, True):
+                assert prng.split(prng.PRNGKey(seed, x64), n, layout) == [
+                    tuple(int(v) for v in k) for k in jax_prng.split(jax_prng.PRNGKey(seed, x64), n, layout)]
     from stochastic_b200.sde_solver import prng_key
-    assert prng_key(5) == (0, 5) and prng_key((3, 4)) == (3, 4) and prng_key(1 << 33) == (2, 0)
+    assert prng_key(5) == (0, 5) and prng_key((3, 4)) == (3, 4)
+    # JAX's integer seeds are int32 unless jax_enable_x64 (jax/_src/prng.py::random_seed): the high key word is 0 and the
+    # seed wraps in 32-bit mode; in 64-bit mode both words of the two's-complement seed are used
+    assert prng_key(-1) == (0, 0xFFFFFFFF) and prng_key(-1, x64=True) == (0xFFFFFFFF, 0xFFFFFFFF)
+    assert prng_key((1 << 33) + 5) == (0, 5) and prng_key((1 << 33) + 5, x64=True) == (2, 5)
+    assert jax_prng.PRNGKey(-1).tolist() == [0, 0xFFFFFFFF] and jax_prng.PRNGKey(-1, x64=True).tolist() == [0xFFFFFFFF] * 2
+    pychastic.config.update("enable_x64", True)
+    try:
+        assert prng_key(1 << 33) == (2, 0)
+    finally:
+        pychastic.config.update("enable_x64", False)
 
 
 def test_warp_specialised_source_selection_and_register_budget():
