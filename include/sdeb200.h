@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDEB200_ABI_VERSION 1
+#define SDEB200_ABI_VERSION 2
 
 typedef struct sdeb200_program sdeb200_program_t; /* a compiled (problem, scheme, dtype) kernel */
 
@@ -69,7 +69,8 @@ typedef struct sdeb200_wiener_args {
 
 /* Mirrors sdeb::BeadArgs (stochastic_b200/csrc/sde_bead_kernel.cuh): Euler-Maruyama Brownian dynamics of a
  * closed chain of N equal beads with RPY mobility, drift = mu (-grad U), noise = sqrt(2) chol(mu) - the built-in
- * functor for reference examples/example_writhed_dna_loop.py:49-86 (stretch + bend + overlap energy). */
+ * functor for reference examples/example_writhed_dna_loop.py:49-86 (stretch + bend + overlap energy, and - for a
+ * program compiled with SDE_BEAD_TWIST - the writhe-dependent twist energy of :57). */
 typedef struct sdeb200_bead_args {
     uint32_t key_a, key_b;
     uint32_t n_fragments, cpr, chunk, n_snapshots;
@@ -83,6 +84,8 @@ typedef struct sdeb200_bead_args {
     double ko;               /* overlap stiffness */
     double sigma2;           /* steric diameter squared */
     double inv_delta2;       /* 1 / (overlap smear width)^2 */
+    double twist_k;          /* twisting stiffness x (2 pi)^2: U_twist = twist_k / 2 (Lk - Wr)^2 (ignored without SDE_BEAD_TWIST) */
+    double linking_number;   /* Lk */
     void* out_t;             /* device (traj_count, n_snapshots)      or NULL */
     void* out_x;             /* device (traj_count, n_snapshots, 3N)  or NULL */
     void* out_w;             /* device (traj_count, n_snapshots, 3N)  or NULL */

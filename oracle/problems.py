@@ -141,9 +141,13 @@ def jfm_four_beads(tmax=8000.0, half=False):
 
 
 def dna_loop(n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., steric_diameter=20.0 / 1111., kbT=1.0,
-             persistence_length=500.0 / 1111., stretch_length=0.037 / 1111., overlap_strength=70.0, tmax=6000.0e-6):
-    """reference `examples/example_writhed_dna_loop.py:25-84` without the twist term (pywrithe is unavailable):
-    energy written as in the example, differentiated by torch autograd."""
+             persistence_length=500.0 / 1111., stretch_length=0.037 / 1111., overlap_strength=70.0, tmax=6000.0e-6,
+             twist=False, linking_number=2.7, x0=None):
+    """reference `examples/example_writhed_dna_loop.py:25-84`: energy written as in the example, differentiated by
+    torch autograd.  `twist=True` includes its twist term (`:57`) with the polygon writhe of `oracle.writhe`
+    (pywrithe itself is unavailable: parity unpinned for that term)."""
+    from . import writhe as owrithe
+    twisting_constant = kbT * persistence_length * (2.0 / 3.0) * beam_length
     n = n_beads
     d0 = beam_length / n
     ks = kbT / (stretch_length * d0)
@@ -160,6 +164,8 @@ def dna_loop(n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., st
         bend = kb * 0.5 * torch.sum(curv ** 2)
         r2 = torch.sum((loc[:, None, :] - loc[None, :, :]) ** 2, dim=-1)
         over = ko * (0.5 * torch.sum(torch.tanh((steric_diameter ** 2 - r2) / delta ** 2) + 1.0) - n)
+        if twist:
+            return ext + bend + over + owrithe.twist_energy(loc, twisting_constant, linking_number)
         return ext + bend + over
 
     def a(x):
@@ -170,9 +176,10 @@ def dna_loop(n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., st
         mu = rpy.muTT_torch(x.reshape(n, 3), radii.to(x.dtype))
         return (2 ** 0.5) * torch.linalg.cholesky(mu)
 
-    k = np.arange(n)
-    x0 = (beam_length / (2 * np.pi)) * np.stack([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), np.zeros(n)], 1)
-    return OracleProblem(a, b, x0.ravel(), tmax, name="dna_loop")
+    if x0 is None:
+        k = np.arange(n)
+        x0 = (beam_length / (2 * np.pi)) * np.stack([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), np.zeros(n)], 1)
+    return OracleProblem(a, b, np.asarray(x0, dtype=np.float64).ravel(), tmax, name="dna_loop")
 
 
 def brownian_rotations(tmax=20.0):

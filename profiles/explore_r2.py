@@ -17,6 +17,7 @@ from stochastic_b200 import workloads, sde_solver
 
 out = {}
 what = set(sys.argv[1:]) or {"hit", "sinh", "snap", "msd", "rot", "host"}
+# "msdlong": the long-time diffusion coefficient of the four-bead chain (reference examples/jfm.py:221: 0.2898)
 
 
 def timed(fn, reps=3):
@@ -36,15 +37,32 @@ if "hit" in what:
     weak = np.loadtxt(os.path.join(G, "weak_convergence_test.csv"), delimiter=",")
     rows = []
     for scheme, col in (("euler", 1), ("milstein", 3), ("wagner_platen", 5)):
-        for n_steps in T.COARSE + [86, 129]:
+        for n_steps in T.N_STEPS:
             row = len(T.N_STEPS) - 1 - T.N_STEPS.index(n_steps)
-            r = T.hitting_time_errors(scheme, n_steps, 200_000)
             r1 = T.hitting_time_errors(scheme, n_steps, 10_000)
+            r = r1
             rows.append(dict(scheme=scheme, n_steps=n_steps, ours=r, ours_10k_seed0=r1, csv_strong=strong[row, col],
                              csv_strong_sigma=strong[row, col + 1], csv_weak=weak[row, col], csv_weak_sigma=weak[row, col + 1]))
             print(scheme, n_steps, "strong %.5f (10k: %.5f) csv %.5f | weak %.5f (10k: %.5f) +- %.5f csv %.5f" % (
-                r["rmse"], r1["rmse"], strong[row, col], abs(r["mean"] - 0.5), abs(r1["mean"] - 0.5), r["mean_std"], weak[row, col]), flush=True)
+                r["rmse"], r1["rmse"], strong[row, col], abs(r["mean"] - 0.5), abs(r1["mean"] - 0.5), r["mean_std"], weak[row, col]),
+                "| 10k: mean_err %.5f err_std %.5f err_std/sqrt(n) %.6f mean_real-0.5 %.5f csv_sigmas %.5f %.6f" % (
+                r1["mean_err"], r1["err_std"], r1["err_std"] / np.sqrt(r1["n"]), r1["mean_real"] - 0.5, strong[row, col + 1], weak[row, col + 1]), flush=True)
     out["hit"] = rows
+
+if "fp" in what:
+    Y_DRIFT, Y_BARRIER = 4.0, 2.0
+    n = 2_000_000
+    for scheme in ("euler", "milstein", "wagner_platen"):
+        for n_steps in (64, 256):
+            prob = workloads.polar_walk(Y_DRIFT, (2.0, 0.0), 2.0, f64=True)
+            solver = pychastic.sde_solver.SDESolver(dt=prob.tmax / n_steps, scheme=scheme)
+            kw = dict(n_trajectories=n, seed=0, chunk_size=None, store_trajectories=False)
+            sol = solver.solve_many(prob, first_passage=lambda x, w, t: x[0] * jnp.sin(x[1]) - Y_BARRIER, **kw)
+            real = solver.solve_many(prob, first_passage=lambda x, w, t: w[1] + Y_DRIFT * t - Y_BARRIER, **kw)
+            both = sol["hit_flag"].torch() & real["hit_flag"].torch()
+            err = (sol["hit_time"].torch() - real["hit_time"].torch())[both]
+            print("fp", scheme, n_steps, "rmse", float(torch.sqrt((err ** 2).mean())), "both", float(both.float().mean()),
+                  "mean real", float(real["hit_time"].torch()[both].mean()), flush=True)
 
 if "sinh" in what:
     import problems as P
@@ -127,6 +145,40 @@ if "msd" in what:
         a = np.polyfit(tt[20:], m[20:, k], 1)[0]
         print(name, "slope*pi", a * np.pi, "max rel dev vs reference csv (256 traj)", rel.max(), "first rows", m[:4, k], ref[:4], flush=True)
     out["msd"] = dict(weights=wts, mstdc=float(mstdc), msd=m.tolist())
+
+if "msdlong" in what:
+    from stochastic_b200 import grpy
+    radii = np.array([3.0, 1.0, 1.0, 1.0])
+    for half in (True, False):
+        prob = workloads.four_beads(tmax=8000.0, half_spring=half, f64=True)
+
+        def trace_mu(x, w, t):
+            mu = grpy.muTT(jnp.reshape(x, (4, 3)), radii)
+            return jnp.array([mu[3 * a + 0][3 * b + 0] + mu[3 * a + 1][3 * b + 1] + mu[3 * a + 2][3 * b + 2]
+                              for a in range(4) for b in range(4)])
+        s = pychastic.sde_solver.SDESolver(dt=0.05)
+        n = 1 << 14
+        t0 = time.perf_counter()
+        sol = s.solve_many(prob, n_trajectories=n, chunk_size=40, chunks_per_randomization=1, seed=0,
+                           store_trajectories=False, observables=trace_mu)
+        tm = (np.asarray(sol["moments"])[:, 0] / n).reshape(4, 4)
+        inv = np.linalg.inv(tm)
+        wts = [float(v) for v in inv.sum(-1) / inv.sum()]
+        print("half", half, "weights", wts, "mstdc", 6.0 / inv.sum(), time.perf_counter() - t0, flush=True)
+
+        def msd(x, w, t, xr):
+            d = x - xr
+            c = [sum(wts[a] * d[3 * a + k] for a in range(4)) for k in range(3)]
+            return jnp.array([d[0] ** 2 + d[1] ** 2 + d[2] ** 2, d[9] ** 2 + d[10] ** 2 + d[11] ** 2,
+                              c[0] ** 2 + c[1] ** 2 + c[2] ** 2])
+        sol = s.solve_many(prob, n_trajectories=n, chunk_size=40, chunks_per_randomization=1, seed=0,
+                           store_trajectories=False, observables=msd, observe_at="snapshots")
+        m = np.asarray(sol["moments"])[:, :, 0] / n
+        tt = 2.0 * np.arange(m.shape[0])
+        for lo, hi in ((20, 200), (200, 1000), (1000, 2000), (2000, 4000), (500, 4000)):
+            print("half", half, "lags", lo * 2, hi * 2, "slope*pi big/small/centre",
+                  [float(np.polyfit(tt[lo:hi], m[lo:hi, k], 1)[0] * np.pi) for k in range(3)], flush=True)
+        out["msdlong_%s" % half] = m[::20].tolist()
 
 if "rot" in what:
     p, post, obs = workloads.evensen_rotations(f64=False)

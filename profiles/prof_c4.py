@@ -1,4 +1,5 @@
-"""C4: 40-bead DNA loop (d = m = 120), Euler dt = 1e-7, final state only.  python profiles/prof_c4.py [n_traj] [steps]"""
+"""C4: 40-bead DNA loop (d = m = 120), Euler dt = 1e-7, final state only.
+python profiles/prof_c4.py [n_traj] [steps]        (TWIST=1: with the writhe-dependent twist energy)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +8,7 @@ from stochastic_b200 import workloads
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-prob = workloads.dna_loop(n_beads=40, tmax=(steps + 0.5) * 1e-7, f64=True)
+prob = workloads.dna_loop(n_beads=40, tmax=(steps + 0.5) * 1e-7, f64=True, twist=bool(int(os.environ.get("TWIST", "0"))))
 solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
 if os.environ.get("BLOCK"):
     solver.block_size = int(os.environ["BLOCK"])

@@ -578,7 +578,8 @@ class SDESolver:
             key_a=ka, key_b=kb, n_fragments=n_frag, cpr=cpr, chunk=chunk, n_snapshots=n_snap, n_traj_total=n_total,
             traj_begin=begin, traj_count=count, x0=x0_dev.data_ptr(), x0_stride=(d if multiple_ic else 0),
             dt=float(self.dt), radius=par["radius"], ks=par["ks"], d0=par["d0"], kb_over_d04=par["kb_over_d04"],
-            ko=par["ko"], sigma2=par["sigma2"], inv_delta2=par["inv_delta2"],
+            ko=par["ko"], sigma2=par["sigma2"], inv_delta2=par["inv_delta2"], twist_k=par.get("twist_k", 0.0),
+            linking_number=par.get("linking_number", 0.0),
             out_t=out_t.data_ptr(), out_x=out_x.data_ptr(), out_w=out_w.data_ptr())
         elem = 8 if f64 else 4
         npad = -(-d // 8) * 8                      # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh

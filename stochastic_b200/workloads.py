@@ -83,9 +83,10 @@ def four_beads(tmax=8000.0, half_spring=False, f64=False):
 
 
 class BeadRingProblem:
-    """Closed chain of N equal beads with RPY hydrodynamic interactions (the writhed-DNA-loop model of
-    reference `examples/example_writhed_dna_loop.py:25-84` without its twist/writhe term, whose dependency
-    `pywrithe` has neither source nor fixture).
+    """Closed chain of N equal beads with RPY hydrodynamic interactions: the writhed-DNA-loop model of
+    reference `examples/example_writhed_dna_loop.py:25-84`.  `twist=True` adds its twist energy
+    `kt/2 (2 pi)^2 (Lk - Wr)^2` (`:36,57`), with the writhe Wr of the bead polygon from `stochastic_b200.writhe`
+    (the reference's `pywrithe.writhe_jax` has neither source nor fixture here: that term is parity-unpinned).
 
     Carries the same attributes as `SDEProblem` (`a`, `b`, `x0`, `tmax`, `dimension`, `noise_terms`) - `a` and
     `b` are the reference's drift / noise written against `stochastic_b200.numpy`, usable by the generic traced
@@ -94,7 +95,7 @@ class BeadRingProblem:
 
     def __init__(self, n_beads=40, beam_length=1.0, hydrodynamic_diameter=28.4 / 1111., steric_diameter=20.0 / 1111.,
                  kbT=1.0, persistence_length=500.0 / 1111., stretch_length=0.037 / 1111., overlap_strength=70.0,
-                 x0=None, tmax=6000.0e-6, f64=False):
+                 x0=None, tmax=6000.0e-6, f64=False, twist=False, linking_number=2.7):
         n = int(n_beads)
         d0 = beam_length / n
         ks = kbT / (stretch_length * d0)
@@ -102,8 +103,13 @@ class BeadRingProblem:
         ko = overlap_strength * kbT
         delta = 0.6 * steric_diameter
         radius = hydrodynamic_diameter / 2.0
+        kt = kbT * persistence_length * (2.0 / 3.0) * beam_length       # twisting stiffness (reference :36)
+        twist_k = kt * 4.0 * np.pi * np.pi if twist else 0.0
+        if twist and n < 4:
+            raise ValueError("the twist term needs at least 4 beads (a triangle has no non-adjacent segments)")
         self.bead_ring = dict(n_beads=n, radius=radius, ks=ks, d0=d0, kb_over_d04=kb / d0 ** 4, ko=ko,
-                              sigma2=steric_diameter ** 2, inv_delta2=1.0 / delta ** 2)
+                              sigma2=steric_diameter ** 2, inv_delta2=1.0 / delta ** 2, twist=bool(twist),
+                              twist_k=twist_k, linking_number=float(linking_number))
         radii = np.full(n, radius)
 
         def u_ene(x):
@@ -114,6 +120,9 @@ class BeadRingProblem:
             bend = kb * 0.5 * jnp.sum(curv2)
             diff = loc[:, None, :] - loc[None, :, :]
             over = ko * (0.5 * jnp.sum(jnp.tanh((steric_diameter ** 2 - jnp.sum(diff ** 2, axis=-1)) / delta ** 2) + 1.0) - n)
+            if twist:
+                from .writhe import writhe
+                return ext + bend + over + 0.5 * twist_k * (linking_number - writhe(loc)) ** 2
             return ext + bend + over
 
         def drift(x):
@@ -140,7 +149,8 @@ class BeadRingProblem:
 
 
 def dna_loop(n_beads=40, tmax=6000.0e-6, f64=False, **kw):
-    """BASELINE config C4 (without the parity-unpinned twist term)."""
+    """BASELINE config C4; `twist=True` for the full energy of the reference example (the twist term is
+    parity-unpinned, see `BeadRingProblem`)."""
     return BeadRingProblem(n_beads=n_beads, tmax=tmax, f64=f64, **kw)
 
 
