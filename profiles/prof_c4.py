@@ -1,5 +1,5 @@
 """C4: 40-bead DNA loop (d = m = 120), Euler dt = 1e-7, final state only.
-python profiles/prof_c4.py [n_traj] [steps]        (TWIST=1: with the writhe-dependent twist energy)"""
+python profiles/prof_c4.py [n_traj] [steps]        (TWIST=1: with the writhe-dependent twist energy; REGTILE=0: shared-memory variant)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,6 +10,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 prob = workloads.dna_loop(n_beads=40, tmax=(steps + 0.5) * 1e-7, f64=True, twist=bool(int(os.environ.get("TWIST", "0"))))
 solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+if os.environ.get("REGTILE"):
+    solver.bead_regtile = bool(int(os.environ["REGTILE"]))
 if os.environ.get("BLOCK"):
     solver.block_size = int(os.environ["BLOCK"])
 for _ in range(2):

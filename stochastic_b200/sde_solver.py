@@ -278,7 +278,19 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
                         stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile), block)
 
 
-def bead_ring_source(n_beads, f64, layout, block, twist=False):
+def bead_regtile_smem_bytes(n_beads, block=128):
+    """Dynamic shared memory of the register-tiled bead kernel; mirrors RT_SMEM_DOUBLES of csrc/sde_bead_kernel.cuh."""
+    npad = -(-3 * n_beads // 8) * 8
+    nt = npad // 8
+    noff = nt * (nt - 1) // 2
+    nbw = block // 32 - 1
+    opw = -(-noff // nbw)
+    mapw = (-(-opw // 5) * 5 + 3) // 4
+    npair = n_beads * (n_beads - 1) // 2
+    return 8 * (6 * npad + (4 + 6 * npair) + 80 * nt + 64 * nt + 72 + (nbw * mapw * 4 + 7) // 8 + (noff + nt) * 16)
+
+
+def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
     """Translation unit of the CTA-per-trajectory bead-chain kernel (csrc/sde_bead_kernel.cuh)."""
     return "\n".join([
         "// generated by stochastic_b200.sde_solver (bead-chain functor)",
@@ -286,6 +298,8 @@ def bead_ring_source(n_beads, f64, layout, block, twist=False):
         f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {block}",
         f"#define SDE_BEAD_DMMA {1 if f64 else 0}",       # fp64: trailing update on the FP64 tensor cores
         f"#define SDE_BEAD_TWIST {1 if twist else 0}",    # writhe-dependent twist energy (reference :57)
+        f"#define SDE_BEAD_REGTILE {1 if regtile else 0}",  # mobility / Cholesky factor in tensor-core accumulator tiles
+        f"#define SDE_BEAD_CHAIN_PER_THREAD {int(os.environ.get('SDEB200_BEAD_CHAIN_PER_THREAD', '0'))}",
         '#include "sde_bead_kernel.cuh"', ""])
 
 
@@ -358,11 +372,12 @@ class SDESolver:
         self.warp_specialize = None    # None: config "warp_specialize"; producer/consumer kernel (sde_kernel_ws.cuh)
         self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
+        self.bead_regtile = None       # None: register-tiled bead kernel whenever it applies (fp64, 3 N <= 128)
 
     # -- kernel selection (shared by compile and solve_many) -----------------------------------
     def _knobs(self):
         return (self.block_size, self.min_blocks_per_sm, self.lockstep, self.snap_tile, self.warp_specialize,
-                tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel,
+                tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel, self.bead_regtile,
                 config.get("warp_specialize"), config.get("reciprocal_division"))
 
     @staticmethod
@@ -378,9 +393,14 @@ class SDESolver:
                 raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
             block = int(self.block_size)
         twist = bool(par.get("twist"))
-        key = ("bead", nb, f64, layout, block, twist)
-        return _cached_plan(key, (), lambda: (KernelSource(bead_ring_source(nb, f64, layout, block, twist), 3 * nb, 0,
-                                                           block, 0, 1), "sde_bead_kernel"))
+        regtile = self.bead_regtile
+        if regtile is None:        # fp64 rings of up to 42 beads: register-tiled Cholesky on the FP64 tensor cores
+            regtile = f64 and 3 * nb <= 128 and block in (128, 256)
+        if regtile and not (f64 and 3 * nb <= 128 and block in (128, 256)):
+            raise ValueError("bead_regtile needs fp64, 3 N <= 128 and 128 or 256 threads per CTA")
+        key = ("bead", nb, f64, layout, block, twist, regtile)
+        return _cached_plan(key, (), lambda: (KernelSource(bead_ring_source(nb, f64, layout, block, twist, regtile),
+                                                           3 * nb, 0, block, 0, 2 if regtile else 1), "sde_bead_kernel"))
 
     def _plan(self, problem, d, f64, layout, post, observe, event, n_snapshots, observe_at, first_sight=None):
         """The (cached) stepping kernel for this problem and these options; `first_sight()` runs before the problem
@@ -582,11 +602,15 @@ class SDESolver:
             linking_number=par.get("linking_number", 0.0),
             out_t=out_t.data_ptr(), out_x=out_x.data_ptr(), out_w=out_w.data_ptr())
         elem = 8 if f64 else 4
-        npad = -(-d // 8) * 8                      # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh
-        lsize = 17 * ((npad // 8) * npad - 4 * (npad // 8) * (npad // 8 - 1)) // 2 + 2
-        smem = (7 * d + 8 + lsize) * elem
+        if plan.ks.traj_per_block == 2:            # register-tiled variant (traj_per_block doubles as its marker)
+            smem = bead_regtile_smem_bytes(nb, block)
+            ctas_per_sm = 2
+        else:
+            npad = -(-d // 8) * 8                  # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh
+            lsize = 17 * ((npad // 8) * npad - 4 * (npad // 8) * (npad // 8 - 1)) // 2 + 2
+            smem = (7 * d + 8 + lsize) * elem
+            ctas_per_sm = max(1, min(8, (220 * 1024) // (smem + 1024)))
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        ctas_per_sm = max(1, min(8, (220 * 1024) // (smem + 1024)))
         runtime.check(runtime.lib().sdeb200_bead_solve(prog.handle, ctypes.byref(args), block, smem,
                                                        sms * ctas_per_sm, runtime.current_stream_ptr()),
                       "sdeb200_bead_solve")

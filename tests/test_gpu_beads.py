@@ -89,3 +89,20 @@ def test_twisted_ring_bead_kernel_equals_generic_traced_kernel(dtype, tol):
         x, y = np.asarray(a[k]), np.asarray(b[k])
         assert x.shape == y.shape and x.dtype == dtype
         assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
+
+
+@pytest.mark.parametrize("twist", [False, True])
+def test_register_tiled_and_shared_memory_variants_agree(twist):
+    """fp64, 40 beads: the register-tiled kernel (mobility and Cholesky factor in tensor-core accumulator fragments,
+    drift from the pair table, noise folded into the panel solves) against the shared-memory variant."""
+    prob = workloads.dna_loop(n_beads=40, tmax=1.2e-6, f64=True, twist=twist, x0=writhed_ring(40))
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
+    assert "SDE_BEAD_REGTILE 1" in solver._bead_plan(prob, True, "original").ks.source
+    solver.bead_regtile = False
+    b = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
+    assert "SDE_BEAD_REGTILE 0" in solver._bead_plan(prob, True, "original").ks.source
+    for k in ("time_values", "solution_values", "wiener_values"):
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
+        assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
