@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDEB200_ABI_VERSION 2
+#define SDEB200_ABI_VERSION 3
 
 typedef struct sdeb200_program sdeb200_program_t; /* a compiled (problem, scheme, dtype) kernel */
 
@@ -86,6 +86,8 @@ typedef struct sdeb200_bead_args {
     double inv_delta2;       /* 1 / (overlap smear width)^2 */
     double twist_k;          /* twisting stiffness x (2 pi)^2: U_twist = twist_k / 2 (Lk - Wr)^2 (ignored without SDE_BEAD_TWIST) */
     double linking_number;   /* Lk */
+    void* workspace;         /* device scratch of the register-tiled variant (SDE_BEAD_REGTILE): 128 bytes per 8x8 tile of
+                                the lower block triangle, written and read by the kernel itself; NULL otherwise */
     void* out_t;             /* device (traj_count, n_snapshots)      or NULL */
     void* out_x;             /* device (traj_count, n_snapshots, 3N)  or NULL */
     void* out_w;             /* device (traj_count, n_snapshots, 3N)  or NULL */

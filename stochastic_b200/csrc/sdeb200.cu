@@ -23,7 +23,7 @@
 
 static_assert(sizeof(sdeb200_solve_args_t) == 120, "sdeb200_solve_args_t layout");
 static_assert(sizeof(sdeb200_wiener_args_t) == 56, "sdeb200_wiener_args_t layout");
-static_assert(sizeof(sdeb200_bead_args_t) == 168, "sdeb200_bead_args_t layout");
+static_assert(sizeof(sdeb200_bead_args_t) == 176, "sdeb200_bead_args_t layout");
 
 namespace {
 

@@ -57,11 +57,11 @@ class BeadArgs(ctypes.Structure):
         ("dt", ctypes.c_double), ("radius", ctypes.c_double), ("ks", ctypes.c_double), ("d0", ctypes.c_double),
         ("kb_over_d04", ctypes.c_double), ("ko", ctypes.c_double), ("sigma2", ctypes.c_double),
         ("inv_delta2", ctypes.c_double), ("twist_k", ctypes.c_double), ("linking_number", ctypes.c_double),
-        ("out_t", ctypes.c_void_p), ("out_x", ctypes.c_void_p), ("out_w", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("out_t", ctypes.c_void_p), ("out_x", ctypes.c_void_p), ("out_w", ctypes.c_void_p),
     ]
 
 
-assert ctypes.sizeof(SolveArgs) == 120 and ctypes.sizeof(WienerArgs) == 56 and ctypes.sizeof(BeadArgs) == 168
+assert ctypes.sizeof(SolveArgs) == 120 and ctypes.sizeof(WienerArgs) == 56 and ctypes.sizeof(BeadArgs) == 176
 
 _lib = None
 _lib_lock = threading.Lock()

@@ -287,7 +287,7 @@ def bead_regtile_smem_bytes(n_beads, block=128):
     opw = -(-noff // nbw)
     mapw = (-(-opw // 5) * 5 + 3) // 4
     npair = n_beads * (n_beads - 1) // 2
-    return 8 * (6 * npad + (4 + 6 * npair) + 80 * nt + 64 * nt + 72 + (nbw * mapw * 4 + 7) // 8 + (noff + nt) * 16)
+    return 8 * (6 * npad + (4 + 6 * npair) + 80 * nt + 64 * nt + 72 + (nbw * mapw * 4 + 7) // 8)
 
 
 def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
@@ -372,7 +372,7 @@ class SDESolver:
         self.warp_specialize = None    # None: config "warp_specialize"; producer/consumer kernel (sde_kernel_ws.cuh)
         self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
-        self.bead_regtile = None       # None: register-tiled bead kernel whenever it applies (fp64, 3 N <= 128)
+        self.bead_regtile = False      # True: register-tiled bead kernel (fp64, 3 N <= 128), see _bead_plan
 
     # -- kernel selection (shared by compile and solve_many) -----------------------------------
     def _knobs(self):
@@ -393,11 +393,17 @@ class SDESolver:
                 raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
             block = int(self.block_size)
         twist = bool(par.get("twist"))
-        regtile = self.bead_regtile
-        if regtile is None:        # fp64 rings of up to 42 beads: register-tiled Cholesky on the FP64 tensor cores
-            regtile = f64 and 3 * nb <= 128 and block in (128, 256)
-        if regtile and not (f64 and 3 * nb <= 128 and block in (128, 256)):
-            raise ValueError("bead_regtile needs fp64, 3 N <= 128 and 128 or 256 threads per CTA")
+        # Register-tiled variant (mobility / Cholesky factor in tensor-core accumulator fragments): opt-in.  Measured on
+        # B200 (profiles/README.md): 7.8e6 against 7.1e6 trajectory-steps/s without the twist term, 4.0e6 against 5.2e6
+        # with it - both variants are bound by the latency of the pivot chain, not by a throughput limit.
+        regtile = bool(self.bead_regtile)
+        if regtile:
+            if not (f64 and 3 * nb <= 128):
+                raise ValueError("bead_regtile needs fp64 and 3 N <= 128")
+            if not self.block_size:
+                block = 160            # chain warp + 4 bulk warps at 128 registers: three CTAs per SM
+            if block not in (128, 160, 192, 224, 256):
+                raise ValueError("bead_regtile: block_size must be 128, 160, 192, 224 or 256")
         key = ("bead", nb, f64, layout, block, twist, regtile)
         return _cached_plan(key, (), lambda: (KernelSource(bead_ring_source(nb, f64, layout, block, twist, regtile),
                                                            3 * nb, 0, block, 0, 2 if regtile else 1), "sde_bead_kernel"))
@@ -599,12 +605,16 @@ class SDESolver:
             traj_begin=begin, traj_count=count, x0=x0_dev.data_ptr(), x0_stride=(d if multiple_ic else 0),
             dt=float(self.dt), radius=par["radius"], ks=par["ks"], d0=par["d0"], kb_over_d04=par["kb_over_d04"],
             ko=par["ko"], sigma2=par["sigma2"], inv_delta2=par["inv_delta2"], twist_k=par.get("twist_k", 0.0),
-            linking_number=par.get("linking_number", 0.0),
+            linking_number=par.get("linking_number", 0.0), workspace=None,
             out_t=out_t.data_ptr(), out_x=out_x.data_ptr(), out_w=out_w.data_ptr())
         elem = 8 if f64 else 4
+        workspace = None
         if plan.ks.traj_per_block == 2:            # register-tiled variant (traj_per_block doubles as its marker)
             smem = bead_regtile_smem_bytes(nb, block)
-            ctas_per_sm = 2
+            ctas_per_sm = 3 if block in (160, 192) else 2
+            npad = -(-d // 8) * 8
+            workspace = torch.empty(((npad // 8) * (npad // 8 + 1) // 2) * 32, dtype=torch.int32, device=dev)
+            args.workspace = workspace.data_ptr()
         else:
             npad = -(-d // 8) * 8                  # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh
             lsize = 17 * ((npad // 8) * npad - 4 * (npad // 8) * (npad // 8 - 1)) // 2 + 2
@@ -619,7 +629,7 @@ class SDESolver:
         self.last_steps = n_snap * chunk
         sol = _Solution(dict(time_values=DeviceArray(out_t), solution_values=DeviceArray(out_x),
                              wiener_values=DeviceArray(out_w)))
-        sol._keepalive = (x0_dev,)
+        sol._keepalive = (x0_dev, workspace)
         return sol
 
     def solve(self, problem, seed=0, chunk_size=1, chunks_per_randomization=None, progress_bar=True):

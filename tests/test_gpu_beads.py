@@ -75,6 +75,19 @@ def test_dna_loop_with_twist_matches_oracle():
     assert np.abs(np.asarray(plain["solution_values"]) - ref["solution_values"]).max() > 1e-7
 
 
+def test_small_rings_on_the_register_tiled_kernel():
+    """5 and 6 beads (2 and 3 tile rows, mostly padding) on the register-tiled kernel against the generic traced one."""
+    for nb in (5, 6):
+        kw = dict(n_beads=nb, beam_length=nb / 40, tmax=2e-6, f64=True, twist=(nb == 6), x0=writhed_ring(nb, nb / 40))
+        solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+        a = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
+        solver.use_bead_kernel = solver.bead_regtile = True
+        b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
+        for k in ("time_values", "solution_values", "wiener_values"):
+            x, y = np.asarray(a[k]), np.asarray(b[k])
+            assert np.abs(x - y).max() <= 1e-9 * max(np.abs(x).max(), 1e-12), (nb, k, np.abs(x - y).max())
+
+
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 5e-4)])
 def test_twisted_ring_bead_kernel_equals_generic_traced_kernel(dtype, tol):
     """Six beads with the twist term: hand-written writhe gradient (bead kernel) vs the symbolic derivative of
@@ -97,12 +110,14 @@ def test_register_tiled_and_shared_memory_variants_agree(twist):
     drift from the pair table, noise folded into the panel solves) against the shared-memory variant."""
     prob = workloads.dna_loop(n_beads=40, tmax=1.2e-6, f64=True, twist=twist, x0=writhed_ring(40))
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
-    a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
-    assert "SDE_BEAD_REGTILE 1" in solver._bead_plan(prob, True, "original").ks.source
-    solver.bead_regtile = False
     b = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
     assert "SDE_BEAD_REGTILE 0" in solver._bead_plan(prob, True, "original").ks.source
-    for k in ("time_values", "solution_values", "wiener_values"):
-        x, y = np.asarray(a[k]), np.asarray(b[k])
-        assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
-        assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
+    solver.bead_regtile = True
+    for block in (None, 128, 256):             # default (160 threads, three CTAs per SM) and the two-CTA variants
+        solver.block_size = block
+        a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
+        assert "SDE_BEAD_REGTILE 1" in solver._bead_plan(prob, True, "original").ks.source
+        for k in ("time_values", "solution_values", "wiener_values"):
+            x, y = np.asarray(a[k]), np.asarray(b[k])
+            assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
+            assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, block, np.abs(x - y).max())
