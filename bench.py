@@ -135,6 +135,20 @@ def cpu_port_rate(n_traj, dt_exp, procs):
     return done / el, el, per * procs
 
 
+def _try_import_jax():
+    """The reference itself needs JAX.  It is not installable in this image (no wheel, no network); if a driver-provided
+    install ever appears (site-packages or baseline/_ref), say so instead of silently timing the port."""
+    for extra in (None, os.path.join(ROOT, "baseline", "_ref")):
+        if extra and os.path.isdir(extra) and extra not in sys.path:
+            sys.path.insert(0, extra)
+        try:
+            import jax  # noqa: F401
+            return True
+        except Exception:
+            continue
+    return False
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -142,6 +156,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_sample, dt_exp = 2000 * procs, 5
+    have_jax = _try_import_jax()
     rates = []
     for _ in range(args.warmup):
         cpu_port_rate(max(procs, n_sample // 16), dt_exp, procs)
@@ -152,15 +167,112 @@ def run_reference(args):
     total = time.perf_counter() - t_all
     value = float(np.mean(rates))
     sample = f"{n_used} trajectories x {2 ** dt_exp} steps (dt=2^-{dt_exp}) of the C2 workload per step, {procs} processes"
+    config = workload_config(N_TRAJ_PER_GPU, args.gpus)
+    # what this arm actually integrates per step: a bounded sample of the workload, not the 10^7 x 1022 of the B200 arm
+    config.update({"n_trajectories_per_gpu": n_used, "n_trajectories_total": n_used, "steps_per_trajectory": 2 ** dt_exp,
+                   "launches_per_step": 1, "outputs": "final t/x/w per trajectory",
+                   "sample_of": "10^7 trajectories x 1022 steps per GPU (the B200 arm's step)",
+                   "parallelism": f"{procs} host processes, one slab of trajectories each"})
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(N_TRAJ_PER_GPU, args.gpus),
+            "config": config,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
                              "note": "numpy/torch.func CPU port of the reference (oracle/); JAX is not installable "
-                                     "here, so the reference itself cannot run"},
+                                     "here, so the reference itself cannot run"
+                                     + (" (a JAX install was found but the pychastic reference arm is not wired to it)"
+                                        if have_jax else "")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs (secondary block of the bench line, N = 1 only)
+# ------------------------------------------------------------------------------------------------
+INSTR_PER_NORMAL = 155        # warp-instructions per fp64 normal (86 threefry + 41 FP64 + 28 other), profiles/README.md
+HBM_PEAK_FALLBACK_GBS = 6650.0
+
+
+def hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def extra_configs(fp64_peak, sm_mhz, budget_s=60.0):
+    """BASELINE configs C1, C3, C4, C5 under the same clock as the headline: one warm-up + best of two launches each,
+    CUDA events.  Every entry states the roofline that bounds it:
+      fp64_fma      algorithmic flops / time against the FP64 FMA peak measured in this run
+      issue_slots   normals/s against 148 SMs x 4 schedulers x clock x 32 lanes / 155 instructions per fp64 normal - the
+                    in-register threefry2x32 + erf_inv generator is what the cheap schemes spend their issue slots on
+      hbm           bytes of stored snapshots / time against the measured HBM copy bandwidth
+      latency       the bead chain: serial pivot chain of the per-step Cholesky factorisation (profiles/README.md)"""
+    import torch
+    import stochastic_b200 as pychastic
+    from stochastic_b200 import workloads
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    normals_peak = sms * 4 * (sm_mhz or 1965.0) * 1e6 * 32 / INSTR_PER_NORMAL
+    hbm_peak, hbm_src = hbm_peak_gbs()
+    rows, t_start = [], time.perf_counter()
+
+    def run(name, prob, scheme, dt, n, flops, normals, bound, **kw):
+        if time.perf_counter() - t_start > budget_s:
+            rows.append({"config": name, "skipped": "time budget of the secondary block exhausted"})
+            return
+        solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
+        for knob, val in kw.pop("knobs", {}).items():
+            setattr(solver, knob, val)
+        best = float("inf")
+        for rep in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            sol = solver.solve_many(prob, n_trajectories=n, seed=0, progress_bar=False, **kw)
+            ev1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, ev0.elapsed_time(ev1))
+            del sol
+        steps = solver.last_steps
+        rate = n * steps / best * 1e3
+        row = {"config": name, "scheme": scheme, "n_trajectories": n, "steps": steps, "ms": round(best, 3), "value": rate,
+               "unit": UNIT, "bound": bound, "fp64_tflops_algorithmic": rate * flops / 1e12,
+               "fp64_frac": rate * flops / 1e12 / fp64_peak, "normals_per_s": rate * normals,
+               "issue_slot_frac": rate * normals / normals_peak}
+        if kw.get("chunk_size", 1) == 1 and kw.get("store_trajectories", True):
+            d, m = prob.dimension, prob.noise_terms
+            row["store_GBps"] = rate * (1 + d + m) * 8 / 1e9
+            row["hbm_frac"] = row["store_GBps"] / hbm_peak
+        row["frac"] = {"fp64_fma": row["fp64_frac"], "issue_slots": row["issue_slot_frac"],
+                       "hbm": row.get("hbm_frac"), "latency": row["fp64_frac"]}[bound]
+        rows.append(row)
+
+    gbm = workloads.gbm(f64=True)
+    for scheme, fl, nn in (("euler", 62, 1), ("milstein", 69, 1), ("wagner_platen", 145, 2)):
+        run("C1 GBM dt=2^-8, 2^21 trajectories, every step stored (3 x 8.6 GB of snapshots)", gbm, scheme, 2 ** -8, 1 << 21,
+            fl, nn, "hbm", chunk_size=1)
+        run("C1 GBM dt=2^-8, 2^24 trajectories, final state only", gbm, scheme, 2 ** -8, 1 << 24, fl, nn, "issue_slots",
+            chunk_size=None)
+    run("C1 GBM dt=2^-8 at its nominal 10^4 trajectories, every step stored (launch-latency bound: 79 CTAs)", gbm, "euler",
+        2 ** -8, 10 ** 4, 62, 1, "hbm", chunk_size=1)
+    polar = workloads.polar_walk(Y_DRIFT, (2.0, 0.0), TMAX, f64=True)
+    run("C2 polar walk dt=2^-7, 10^7 trajectories, final only", polar, "euler", 2 ** -7, 10 ** 7, 150, 2, "issue_slots",
+        chunk_size=None)
+    run("C2 polar walk dt=2^-7, 10^7 trajectories, final only", polar, "milstein", 2 ** -7, 10 ** 7, 2500, 44,
+        "issue_slots", chunk_size=None)
+    run("C3 two RPY spheres dt=0.01, 10^6 trajectories x 500 steps, final only", workloads.two_spheres(tmax=5.0, f64=True),
+        "euler", 0.01, 10 ** 6, 650, 6, "issue_slots", chunk_size=None)
+    for twist, fl in ((False, 0.70e6), (True, 0.87e6)):
+        run("C4 writhed DNA loop (40 beads, d = m = 120)" + (" with" if twist else " without") + " the twist term, 8880 x 100 steps",
+            workloads.dna_loop(n_beads=40, tmax=100.5e-7, f64=True, twist=twist), "euler", 1e-7, 8880, fl, 120, "latency",
+            chunk_size=None)
+    run("C5 GARCH/Heston call payoff dt=0.01, 10^8 paths x 200 steps, moments only (1/10 of the 10^9-path job per GPU-slot)",
+        workloads.garch(f64=True), "wagner_platen", 0.01, 10 ** 8, 10900, 46, "fp64_fma", chunk_size=None,
+        observables=workloads.call_payoff(120.0), store_trajectories=False)
+    return {"configs": rows, "normals_peak_per_s": normals_peak, "instr_per_normal": INSTR_PER_NORMAL,
+            "hbm_peak_GBps": hbm_peak, "hbm_peak_source": hbm_src, "fp64_peak_tflops": fp64_peak,
+            "note": "builder's secondary block (not part of the timed headline): each config once warm, best of two"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -279,6 +391,12 @@ def run_b200(args):
         ey = x[:, 0] * torch.sin(x[:, 1]) - (w[:, 1] + Y_DRIFT * tt)
         medians.append(float(torch.median(torch.hypot(ex, ey)).item()))
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            extra = extra_configs(fp64_peak, (clocks or {}).get("sm_mhz"))
+        except Exception as exc:          # the secondary block must never cost the headline line
+            extra = {"error": repr(exc)}
     if rank == 0:
         mom = moments.cpu().numpy()
         n_all = float(n_total)
@@ -300,6 +418,9 @@ def run_b200(args):
                 "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp64_peak,
                              "traffic": DRAM_BYTES_PER_DOMINANT_LAUNCH if n_local == N_TRAJ_PER_GPU else None,
+                             "traffic_source": "static: ncu capture of this launch committed under profiles/ (not re-measured "
+                                               "in this run); kernel_ms, achieved, peak and frac are live",
+                             "executed_source": "static: ncu instruction counts of the committed capture x the live kernel rate",
                              "traffic_note": "dram__bytes_read+write of this launch from ncu (round-1 capture, "
                                              "profiles/r1_ncu_c2_ws_bench_kernel_traffic.csv); algorithmic bytes are the "
                                              "400 MB of final states - the kernel is FP64/issue-bound, not HBM-bound",
@@ -318,7 +439,7 @@ def run_b200(args):
                              "note": "strong error = |cartesian(x_T) - exact Brownian path|; the mean is dominated by "
                                      "the rare trajectories that step across the r = 0 coordinate singularity (as in "
                                      "the reference), the median (first 2^20 trajectories of rank 0) shows the order"},
-                "kernel_registers": solvers[e].last_program.info()["registers"]}
+                "kernel_registers": solvers[e].last_program.info()["registers"], "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-traj", type=int, default=N_TRAJ_PER_GPU, help="trajectories per GPU (default: 10^7, the BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary block (other BASELINE configs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

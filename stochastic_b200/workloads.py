@@ -186,6 +186,10 @@ def precompile_all():
         jobs.append((four_beads(f64=f64), "euler", None))
     jobs.append((garch(f64=True), "wagner_platen", call_payoff()))
     jobs.append((polar_walk(4.0, (2.0, 0.0), f64=True), "wagner_platen", polar_error_observables(4.0, 2.0)))
+    for twist in (False, True):            # C4: the CTA-per-trajectory bead kernels
+        for f64 in (True, False):
+            SDESolver(scheme="euler", dt=1e-7).compile(dna_loop(n_beads=40, f64=f64, twist=twist))
+            n += 1
     for prob, scheme, obs in jobs:
         # final-only launches (chunk_size=None) and every-step snapshots (the reference's default chunk_size=1)
         for chunk_size in (None, 1):
