@@ -170,20 +170,22 @@ def test_shared_memory_size_formula_matches_the_header():
     assert 3 * (bead_regtile_smem_bytes(40, 192) + 1024) <= 227 * 1024
 
 
+@pytest.mark.parametrize("nbw", [3, 4, 5, 6, 7])
 @pytest.mark.parametrize("nb", [5, 6, 11, 40, 42])
-def test_bulk_warp_tile_maps(nb):
+def test_bulk_warp_tile_maps(nb, nbw):
     """The packed tile maps of the bulk warps (sde_bead_kernel: `map[q]`): every off-diagonal tile exactly once, dealt
     round-robin in column-major order, so that for each warp the column index never decreases along its slots - the
     property the chunk-wise skipping of finished tiles relies on - and unused slots are (0, 0)."""
     NT = -(-3 * nb // 8)
     noff = NT * (NT - 1) // 2
-    opw = (noff + 2) // 3
+    opw = -(-noff // nbw)
     mapw = (-(-opw // 5) * 5 + 3) // 4
     seen = []
-    for w in range(3):
+    for w in range(nbw):
         last_j = 0
+        slots = []
         for k in range(mapw * 4):
-            o = w + 3 * k
+            o = w + nbw * k
             v = 0
             if k < opw and o < noff:
                 J, rem = 0, o
@@ -192,12 +194,21 @@ def test_bulk_warp_tile_maps(nb):
                     J += 1
                 v = (J + 1 + rem) | (J << 4)
             I, J = v & 15, v >> 4
+            slots.append((I, J, bool(v)))
             if v:
                 assert NT > I > J >= last_j
                 last_j = J
                 seen.append((I, J))
             else:
                 assert (I, J) == (0, 0)
+        # the chunk-activity test of the trailing update (`jlast`): for every panel p a chunk is entered iff it
+        # holds an active tile
+        for p in range(NT):
+            for ch in range(-(-opw // 5)):
+                last = min(ch * 5 + 4, opw - 1)
+                jlast = slots[last][1] if (w + nbw * last < noff or last == 0) else slots[max(last - 1, 0)][1]
+                truth = any(valid and J > p for (I, J, valid) in slots[ch * 5:ch * 5 + 5])
+                assert (jlast > p) == truth, (nb, nbw, w, p, ch)
     assert sorted(seen) == sorted((I, J) for J in range(NT) for I in range(J + 1, NT))
 
 
