@@ -15,6 +15,10 @@ _STATE = {
     # divisions become multiplications (an FP64 division costs ~12 instructions on the GPU).  Changes the last bit of
     # those quotients, so it is opt-in: the default keeps the operations the user's functions spell out.
     "reciprocal_division": False,
+    # Stored trajectories: hand whole snapshot tiles (32 trajectories x 16..128 bytes per field column) to the TMA
+    # unit (csrc/sde_snap_tma.cuh) whenever the output rows are 16-byte multiples.  False: the warp-transposed
+    # write-out loop of csrc/sde_kernel.cuh (also the fallback for rows a tensor map cannot describe).
+    "snapshot_tma": True,
 }
 
 

@@ -33,6 +33,9 @@
 #ifndef SDE_SNAP_TILE
 #define SDE_SNAP_TILE 1     // > 1: stage this many consecutive snapshots per trajectory in shared memory
 #endif
+#ifndef SDE_SNAP_TMA
+#define SDE_SNAP_TMA 0      // > 0: snapshot tiles of this many snapshots leave through the TMA unit (sde_snap_tma.cuh)
+#endif
 #define SDE_SNAP_FIELDS (1 + SDE_D + SDE_M)
 #define SDE_SNAP_PITCH 33   // lane pitch of a staged row (bank-conflict padding)
 #ifndef SDE_LOCKSTEP
@@ -40,6 +43,7 @@
 #endif
 
 #include "sde_hooks.cuh"
+#include "sde_snap_tma.cuh"
 
 namespace sdeb {
 
@@ -70,13 +74,22 @@ struct SolveArgs {
 // dynamic shared memory: SDE_STAGE_COUNT rows of SDE_BLOCK reals (the normals staging area)
 extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
 
+#if SDE_SNAP_TMA
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solve_kernel(const sdeb::SolveArgs A,
+                                                                                        const __grid_constant__ sdeb::SnapMaps TM) {
+#else
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solve_kernel(const sdeb::SolveArgs A) {
+#endif
     using namespace sdeb;
 #if SDE_LOGTAB_IN_SMEM
     sde_fill_logtab();
 #endif
     real* const stage = reinterpret_cast<real*>(sde_dyn_smem) + threadIdx.x;
-#if SDE_SNAP_TILE > 1
+#if SDE_SNAP_TMA
+    SnapWriter snapw;
+    snapw.init(sde_dyn_smem + (size_t)SDE_STAGE_COUNT * SDE_BLOCK * sizeof(real), threadIdx.x >> 5, threadIdx.x & 31,
+               (u64)blockIdx.x * SDE_BLOCK + (threadIdx.x & ~31u));
+#elif SDE_SNAP_TILE > 1
     // Snapshot staging: the thread-per-trajectory mapping would store 8 bytes at a stride of a whole trajectory
     // row.  Instead every warp collects SDE_SNAP_TILE consecutive snapshots of its 32 trajectories in shared
     // memory and writes them out transposed, so that one store instruction covers contiguous
@@ -185,7 +198,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
 #if SDE_NOBS > 0 && SDE_OBS_SNAP
                     if (A.moments) observe_accumulate_warp(x, w, t, xref, active, A.moments + (u64)snap * (2 * SDE_NOBS));
 #endif
-#if SDE_SNAP_TILE > 1
+#if SDE_SNAP_TMA
+                    snapw.snapshot(A, TM, snap, t, x, w);
+#elif SDE_SNAP_TILE > 1
                 {
                     real* col = snapbuf + tile_fill * SDE_SNAP_PITCH + lane;
                     col[0] = t;
@@ -265,6 +280,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_solv
 #endif
 #if SDE_NOBS > 0 && !SDE_OBS_SNAP
         sde_observe(x, w, t, xref, obs);
+#endif
+#if SDE_SNAP_TMA
+        snapw.finish();
 #endif
     }
 #if SDE_NOBS > 0 && !SDE_OBS_SNAP

@@ -52,7 +52,12 @@ static_assert(SDE_BLOCK == SDE_WS_NC + SDE_WS_NP, "SDE_BLOCK must be 128 consume
 static_assert(SDE_STAGE_STRIDE == SDE_WS_NC, "staging rows hold one value per consumer");
 static_assert(SDE_STAGE_COUNT > 0, "warp specialisation is for staged generators");
 
+#ifndef SDE_SNAP_TMA
+#define SDE_SNAP_TMA 0                // > 0: the consumers' snapshots leave in tiles through the TMA unit (sde_snap_tma.cuh)
+#endif
+
 #include "sde_hooks.cuh"
+#include "sde_snap_tma.cuh"
 
 namespace sdeb {
 
@@ -79,7 +84,12 @@ __device__ __forceinline__ void st_shared(u32 addr, float v) { asm volatile("st.
 
 extern __shared__ __align__(16) unsigned char sde_dyn_smem[];
 
+#if SDE_SNAP_TMA
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(const sdeb::SolveArgs A,
+                                                                            const __grid_constant__ sdeb::SnapMaps TM) {
+#else
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(const sdeb::SolveArgs A) {
+#endif
     using namespace sdeb;
     constexpr int NC = SDE_WS_NC, NP = SDE_WS_NP, ALL = SDE_BLOCK;
     constexpr int FULL0 = 1, EMPTY0 = 3, CONS = 5;            // named barrier ids (0 is __syncthreads)
@@ -225,6 +235,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 #pragma unroll
         for (int i = 0; i < SDE_D; ++i) hit_x[i] = RC(0.0);
 #endif
+#if SDE_SNAP_TMA
+        // snapshot tiles of the four consumer warps live behind the ring
+        SnapWriter snapw;
+        snapw.init(sde_dyn_smem + (size_t)2 * SDE_STAGE_COUNT * NC * sizeof(real), threadIdx.x >> 5, threadIdx.x & 31,
+                   (u64)blockIdx.x * NC + (threadIdx.x & ~31u));
+#endif
         WienerGen gen;                                         // without consumer-drawn normals only S is used here
         gen.S = S;
         u32 snap = 0, in_chunk = 0;
@@ -300,6 +316,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
 #if SDE_NOBS > 0 && SDE_OBS_SNAP
             if (A.moments) observe_accumulate_warp(x, w, t, xref, active, A.moments + (u64)snap * (2 * SDE_NOBS));
 #endif
+#if SDE_SNAP_TMA
+            snapw.snapshot(A, TM, snap, t, x, w);
+#else
             if (active) {
                 const u64 row = tid * (u64)A.n_snapshots + snap;
                 if (A.out_t) A.out_t[row] = t;
@@ -312,8 +331,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                     for (int j = 0; j < SDE_M; ++j) A.out_w[row * SDE_M + j] = w[j];
                 }
             }
+#endif
             ++snap;
         }
+#if SDE_SNAP_TMA
+        snapw.finish();
+#endif
 #if SDE_HAS_EVENT
         if (active && A.out_hit) {
             real* o = A.out_hit + tid * (u64)(2 + SDE_D);

@@ -45,6 +45,11 @@ struct Driver {
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+    CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -71,6 +76,9 @@ Driver& driver() {
         BIND(FuncGetAttribute, "cuFuncGetAttribute")
         BIND(FuncSetAttribute, "cuFuncSetAttribute")
         BIND(GetErrorString, "cuGetErrorString")
+        BIND(ModuleGetGlobal, "cuModuleGetGlobal_v2")
+        BIND(MemcpyDtoH, "cuMemcpyDtoH_v2")
+        BIND(TensorMapEncodeTiled, "cuTensorMapEncodeTiled")
 #undef BIND
         d.ok = true;
     });
@@ -151,9 +159,14 @@ struct sdeb200_program {
     CUmodule module = nullptr;
     CUfunction func = nullptr;
     size_t smem_optin = 0;  // largest dynamic shared memory size already opted in for
+    // kernels whose snapshots leave through the TMA unit (csrc/sde_snap_tma.cuh) export `sde_snap_tma_info`:
+    // {snapshots per tile, sizeof(real), d, m, CUtensorMapSwizzle}; tile == 0: the kernel takes no tensor maps
+    int tma[5] = {0, 0, 0, 0, 0};
 };
 
 namespace {
+struct alignas(64) SnapMaps { CUtensorMap t, x, w; };   // second kernel parameter of TMA-storing kernels (sdeb::SnapMaps)
+
 int ensure_smem(sdeb200_program* p, size_t bytes) {
     if (bytes <= 48 * 1024 || bytes <= p->smem_optin) return 0;
     if (bytes > 227 * 1024) return fail(-1, "dynamic shared memory request exceeds 227 KB");
@@ -257,6 +270,18 @@ int sdeb200_program_load(const void* cubin, size_t cubin_size, const char* entry
         delete p;
         return fail(3, std::string("cuModuleGetFunction(") + entry + "): " + cu_err(r));
     }
+    {   // optional module global: snapshot tiles stored by the TMA unit
+        CUdeviceptr g = 0;
+        size_t bytes = 0;
+        if (d.ModuleGetGlobal(&g, &bytes, p->module, "sde_snap_tma_info") == CUDA_SUCCESS && bytes == sizeof(p->tma)) {
+            r = d.MemcpyDtoH(p->tma, g, sizeof(p->tma));
+            if (r != CUDA_SUCCESS) {
+                d.ModuleUnload(p->module);
+                delete p;
+                return fail(3, "cuMemcpyDtoH(sde_snap_tma_info): " + cu_err(r));
+            }
+        }
+    }
     *out = p;
     return 0;
 }
@@ -296,7 +321,34 @@ int sdeb200_solve(sdeb200_program_t* prog, const sdeb200_solve_args_t* args, int
     if (grid > 0x7fffffffULL) return fail(-1, "sdeb200_solve: too many trajectories for one launch");
     if (int e = ensure_smem(prog, dyn_smem_bytes)) return e;
     sdeb200_solve_args_t a = *args;
-    void* params[] = {&a};
+    SnapMaps maps;
+    void* params[] = {&a, &maps};
+    if (prog->tma[0] > 0) {
+        // (trajectory, n_snapshots * width) views of the three output arrays, boxes of 32 trajectories x one tile row
+        const int tile = prog->tma[0], elem = prog->tma[1], width[3] = {1, prog->tma[2], prog->tma[3]};
+        void* const out[3] = {a.out_t, a.out_x, a.out_w};
+        CUtensorMap* const map[3] = {&maps.t, &maps.x, &maps.w};
+        if (((uint64_t)a.n_snapshots * (uint64_t)elem) % 16)
+            return fail(-1, "sdeb200_solve: this program stores snapshots through the TMA unit, which needs "
+                            "n_snapshots * sizeof(real) to be a multiple of 16 bytes");
+        for (int f = 0; f < 3; ++f) {
+            memset(map[f], 0, sizeof(CUtensorMap));
+            if (!out[f]) continue;
+            if ((uintptr_t)out[f] % 16)
+                return fail(-1, "sdeb200_solve: this program stores snapshots through the TMA unit, which needs "
+                                "16-byte aligned output arrays");
+            const cuuint64_t dims[2] = {(cuuint64_t)a.n_snapshots * (cuuint64_t)width[f], (cuuint64_t)a.traj_count};
+            const cuuint64_t strides[1] = {dims[0] * (cuuint64_t)elem};
+            const cuuint32_t box[2] = {(cuuint32_t)tile, 32u}, estr[2] = {1u, 1u};
+            if (dims[0] > 0xffffffffULL || dims[1] > 0xffffffffULL)
+                return fail(-1, "sdeb200_solve: output array too large for a tensor map");
+            CUresult r = driver().TensorMapEncodeTiled(
+                map[f], elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out[f], dims,
+                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)prog->tma[4],
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(3, "cuTensorMapEncodeTiled: " + cu_err(r));
+        }
+    }
     CUresult r = driver().LaunchKernel(prog->func, (unsigned)grid, 1, 1, (unsigned)block, 1, 1,
                                        (unsigned)dyn_smem_bytes, (CUstream)stream, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(3, "cuLaunchKernel(sde_solve_kernel): " + cu_err(r));

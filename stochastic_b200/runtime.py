@@ -151,6 +151,26 @@ def snap_tile_bytes(d, m, block, f64, tile):
     return 0 if tile <= 1 else (block // 32) * (1 + d + m) * tile * 33 * (8 if f64 else 4)
 
 
+def pick_snap_tma(d, m, warps, f64, other_bytes, n_snapshots, budget=96 * 1024):
+    """Snapshot tiles stored by the TMA unit (csrc/sde_snap_tma.cuh): (snapshots per tile, CUtensorMapSwizzle), or
+    (0, 0) when the output rows cannot be described by a tensor map (n_snapshots * sizeof(real) not a multiple of
+    16 bytes) or no tile fits.  Tile rows are 128, 64, 32 or 16 bytes; the largest that is not longer than the run
+    and whose boxes (`warps` x (1 + d + m) x 32 rows, plus 1 KB of alignment slack) fit in `budget` bytes per CTA
+    next to `other_bytes` of other dynamic shared memory."""
+    elem = 8 if f64 else 4
+    if n_snapshots < 4 or (n_snapshots * elem) % 16:
+        return 0, 0
+    for swz, rowb in ((3, 128), (2, 64), (1, 32), (0, 16)):
+        tile = rowb // elem
+        if tile <= n_snapshots and other_bytes + snap_tma_bytes(d, m, warps, f64, tile) <= budget:
+            return tile, swz
+    return 0, 0
+
+
+def snap_tma_bytes(d, m, warps, f64, tile):
+    return 0 if tile < 1 else 1024 + warps * (1 + d + m) * 32 * tile * (8 if f64 else 4)
+
+
 def check(status, what=""):
     if status == 0:
         return
@@ -185,7 +205,7 @@ def nvrtc_version():
 def _core_fingerprint():
     h = hashlib.sha256()
     h.update("nvrtc %d.%d\n".encode() % nvrtc_version()[:2])      # cubins of different compilers never mix
-    for name in ("sde_core.cuh", "sde_hooks.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh",
+    for name in ("sde_core.cuh", "sde_hooks.cuh", "sde_snap_tma.cuh", "sde_kernel.cuh", "sde_kernel_ws.cuh", "sde_wiener_kernel.cuh",
                  "sde_bead_kernel.cuh"):
         with open(os.path.join(CSRC_DIR, name), "rb") as f:
             h.update(f.read())

@@ -235,6 +235,17 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
             # ptxas 12.9 crashes on a call to the out-of-line erf_inv tail from the register-grown consumer branch
             parts.append("#define SDE_TAIL_ATTR __forceinline__")
         ring_bytes = 2 * stage * 128 * elem
+        # stored trajectories: snapshot tiles of the four consumer warps behind the ring, as large as two CTAs per SM
+        # leave room for (228 KB per SM, 1 KB reserved per CTA, 1 KB of static shared memory for the log table)
+        tma_tile = tma_swz = 0
+        if isinstance(snap_tile, tuple):
+            _, tma_tile, tma_swz = snap_tile
+        elif snap_tile is None and config.get("snapshot_tma"):
+            tma_tile, tma_swz = runtime.pick_snap_tma(d, m, 4, f64, ring_bytes, n_snapshots, budget=(228 // 2 - 2) * 1024)
+        if tma_tile:
+            parts.append(f"#define SDE_SNAP_TMA {int(tma_tile)}")
+            parts.append(f"#define SDE_SNAP_SWZ {int(tma_swz)}")
+            ring_bytes += runtime.snap_tma_bytes(d, m, 4, f64, tma_tile)
         n_obs, hooks = _emit_hooks(parts, d, m, f64, post, observe, event, observe_at)
         parts.append('#include "sde_core.cuh"')
         parts.append(f'static_assert(SDE_STAGE_COUNT == {stage}, "host/device staging size mismatch");')
@@ -260,7 +271,22 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {int(block)}",
     ]
     stage_bytes = stage * block * elem
-    if snap_tile is None:
+    # snapshot write-out: tiles through the TMA unit when the output rows can be described by a tensor map
+    # (snap_tile = None or ("tma", tile, swizzle)), else a transposed write-out of `snap_tile` staged snapshots, else
+    # direct stores
+    tma_tile = tma_swz = 0
+    if snap_tile is None and config.get("snapshot_tma"):
+        # kernels capped at six CTAs per SM (small step functions) keep that occupancy: measured on B200, C1 with every
+        # step stored runs at 3.67 TB/s with 64-byte rows and six CTAs against 3.42 TB/s with 128-byte rows and four
+        budget = (227 * 1024) // 6 - 2048 if min_blocks == 6 else 96 * 1024
+        tma_tile, tma_swz = runtime.pick_snap_tma(d, m, block // 32, f64, stage_bytes, n_snapshots, budget=budget)
+    elif isinstance(snap_tile, tuple):
+        _, tma_tile, tma_swz = snap_tile
+    if tma_tile:
+        snap_tile = 1
+        parts.append(f"#define SDE_SNAP_TMA {int(tma_tile)}")
+        parts.append(f"#define SDE_SNAP_SWZ {int(tma_swz)}")
+    elif snap_tile is None:
         snap_tile = runtime.pick_snap_tile(d, m, block, f64, stage_bytes, n_snapshots)
     if snap_tile > 1:
         parts.append(f"#define SDE_SNAP_TILE {int(snap_tile)}")
@@ -275,19 +301,23 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     parts += hooks
     parts.append('#include "sde_kernel.cuh"')
     return KernelSource("\n".join(parts) + "\n", m, n_obs, block,
-                        stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile), block)
+                        stage_bytes + runtime.snap_tile_bytes(d, m, block, f64, snap_tile) +
+                        runtime.snap_tma_bytes(d, m, block // 32, f64, tma_tile), block)
 
 
-def bead_regtile_smem_bytes(n_beads, block=128):
+def bead_regtile_block(n_beads):
+    """Threads per CTA of the register-tiled bead kernel: one chain warp and NT / 2 bulk warps (NT = tile rows of 8)."""
+    nt = -(-3 * n_beads // 8)
+    return 32 * (1 + max(1, nt // 2))
+
+
+def bead_regtile_smem_bytes(n_beads):
     """Dynamic shared memory of the register-tiled bead kernel; mirrors RT_SMEM_DOUBLES of csrc/sde_bead_kernel.cuh."""
     npad = -(-3 * n_beads // 8) * 8
     nt = npad // 8
-    noff = nt * (nt - 1) // 2
-    nbw = block // 32 - 1
-    opw = -(-noff // nbw)
-    mapw = (-(-opw // 5) * 5 + 3) // 4
     npair = n_beads * (n_beads - 1) // 2
-    return 8 * (6 * npad + (4 + 6 * npair) + 80 * nt + 64 * nt + 72 + (nbw * mapw * 4 + 7) // 8)
+    dch = max(3, min(6, bead_regtile_block(n_beads) // n_beads))          # drift chunks per bead (RT_DCH)
+    return 8 * ((8 + dch) * npad + (4 + 6 * npair) + npair + (npair & 1) + 2 * nt * 64 + 128)
 
 
 def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
@@ -300,6 +330,8 @@ def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
         f"#define SDE_BEAD_TWIST {1 if twist else 0}",    # writhe-dependent twist energy (reference :57)
         f"#define SDE_BEAD_REGTILE {1 if regtile else 0}",  # mobility / Cholesky factor in tensor-core accumulator tiles
         f"#define SDE_BEAD_CHAIN_PER_THREAD {int(os.environ.get('SDEB200_BEAD_CHAIN_PER_THREAD', '0'))}",
+        f"#define SDE_BEAD_TIMING {int(os.environ.get('SDEB200_BEAD_TIMING', '0'))}",   # diagnostics: per-phase cycle counts
+        *([f"#define SDE_BEAD_EXPERIMENT_SKIP {int(os.environ['SDEB200_BEAD_SKIP'])}"] if os.environ.get("SDEB200_BEAD_SKIP") else []),
         '#include "sde_bead_kernel.cuh"', ""])
 
 
@@ -372,13 +404,13 @@ class SDESolver:
         self.warp_specialize = None    # None: config "warp_specialize"; producer/consumer kernel (sde_kernel_ws.cuh)
         self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
-        self.bead_regtile = False      # True: register-tiled bead kernel (fp64, 3 N <= 128), see _bead_plan
+        self.bead_regtile = None       # register-tiled bead kernel: None = whenever it applies (fp64, 3 N <= 128), see _bead_plan
 
     # -- kernel selection (shared by compile and solve_many) -----------------------------------
     def _knobs(self):
         return (self.block_size, self.min_blocks_per_sm, self.lockstep, self.snap_tile, self.warp_specialize,
                 tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel, self.bead_regtile,
-                config.get("warp_specialize"), config.get("reciprocal_division"))
+                config.get("warp_specialize"), config.get("reciprocal_division"), config.get("snapshot_tma"))
 
     @staticmethod
     def _uses_bead_kernel(problem, force):
@@ -393,17 +425,17 @@ class SDESolver:
                 raise ValueError(f"bead kernel: block_size must be a multiple of 32 in [{block}, 1024]")
             block = int(self.block_size)
         twist = bool(par.get("twist"))
-        # Register-tiled variant (mobility / Cholesky factor in tensor-core accumulator fragments): opt-in.  Measured on
-        # B200 (profiles/README.md): 7.8e6 against 7.1e6 trajectory-steps/s without the twist term, 4.0e6 against 5.2e6
-        # with it - both variants are bound by the latency of the pivot chain, not by a throughput limit.
-        regtile = bool(self.bead_regtile)
+        # Register-tiled variant (mobility / Cholesky factor in tensor-core accumulator fragments, fraction-free pivot
+        # chain, row solves as tensor-core products): the default wherever it applies.  Measured on B200
+        # (profiles/README.md, 8 880 x 100 steps): 1.07e7 against 7.3e6 trajectory-steps/s without the twist term,
+        # 6.4e6 against 5.3e6 with it.
+        regtile = (f64 and 3 * nb <= 128) if self.bead_regtile is None else bool(self.bead_regtile)
         if regtile:
             if not (f64 and 3 * nb <= 128):
                 raise ValueError("bead_regtile needs fp64 and 3 N <= 128")
-            if not self.block_size:
-                block = 160            # chain warp + 4 bulk warps at 128 registers: three CTAs per SM
-            if block not in (128, 160, 192, 224, 256):
-                raise ValueError("bead_regtile: block_size must be 128, 160, 192, 224 or 256")
+            if self.block_size and self.block_size != bead_regtile_block(nb):
+                raise ValueError(f"bead_regtile: the block size is fixed by the ring size ({bead_regtile_block(nb)} threads)")
+            block = bead_regtile_block(nb)
         key = ("bead", nb, f64, layout, block, twist, regtile)
         return _cached_plan(key, (), lambda: (KernelSource(bead_ring_source(nb, f64, layout, block, twist, regtile),
                                                            3 * nb, 0, block, 0, 2 if regtile else 1), "sde_bead_kernel"))
@@ -411,7 +443,8 @@ class SDESolver:
     def _plan(self, problem, d, f64, layout, post, observe, event, n_snapshots, observe_at, first_sight=None):
         """The (cached) stepping kernel for this problem and these options; `first_sight()` runs before the problem
         is traced for the first time."""
-        snap_class = min(int(n_snapshots), 16)             # all that pick_snap_tile reads of the snapshot count
+        # all that pick_snap_tile / pick_snap_tma read of the snapshot count
+        snap_class = (min(int(n_snapshots), 32), (int(n_snapshots) * (8 if f64 else 4)) % 16 == 0)
         key = ("step", id(problem.a), id(problem.b), d, self.scheme, f64, layout, id(post) if post else None,
                id(observe) if observe else None, id(event) if event else None, observe_at, snap_class, self._knobs())
         return _cached_plan(key, (problem.a, problem.b, post, observe, event), lambda: (
@@ -610,8 +643,8 @@ class SDESolver:
         elem = 8 if f64 else 4
         workspace = None
         if plan.ks.traj_per_block == 2:            # register-tiled variant (traj_per_block doubles as its marker)
-            smem = bead_regtile_smem_bytes(nb, block)
-            ctas_per_sm = 3 if block in (160, 192) else 2
+            smem = bead_regtile_smem_bytes(nb)
+            ctas_per_sm = max(1, min(2 if block > 170 else 3, (227 * 1024) // (smem + 1024)))
             npad = -(-d // 8) * 8
             workspace = torch.empty(((npad // 8) * (npad // 8 + 1) // 2) * 32, dtype=torch.int32, device=dev)
             args.workspace = workspace.data_ptr()

@@ -1,36 +1,101 @@
-"""Host model of the register-tiled bead kernel (csrc/sde_bead_kernel.cuh, SDE_BEAD_REGTILE): the same tile map,
+"""Host model of the register-tiled bead kernel (csrc/sde_bead_kernel.cuh, SDE_BEAD_REGTILE): the same tile ownership,
 fragment layouts, buffer indexing and phase order, executed lane by lane in numpy.  Checks that the data flow of the
-kernel - mobility tiles built from the pair table in accumulator-fragment order, raw buffer, diagonal factor, row
-solves written in operand-fragment order, DMMA trailing updates, noise folded into the row solves, drift from the pair
+kernel - mobility tiles built from the pair table in accumulator-fragment order, the fraction-free factorisation of the
+diagonal tile with its inverse, the row solves as tensor-core products with a permuted contraction index, the
+double-buffered panel, the catch-up of the diagonal tiles, noise folded into the row solves, drift from the pair
 table - computes chol(mu) xi and mu F.  (The arithmetic itself is checked on the GPU against the oracle.)"""
+import re
+
 import numpy as np
 import pytest
 
 from oracle import rpy
 
+LANES = np.arange(32)
+ROW, QD = LANES >> 2, LANES & 3
+OFF = 8 * ROW + 2 * QD                      # a lane's two entries of a row-major 8x8 tile
+
 
 def dmma884(c, a, b):
-    """mma.m8n8k4.row.col.f64 on 32-lane fragments: c (32, 2), a (32,), b (32,)."""
+    """mma.m8n8k4.row.col.f64 on 32-lane fragments: c (32, 2), a (32,) = A[l/4][l%4], b (32,) = B[l%4][l/4]."""
     A = np.zeros((8, 4))
     B = np.zeros((4, 8))
-    for l in range(32):
-        A[l >> 2, l & 3] = a[l]
-        B[l & 3, l >> 2] = b[l]
+    A[ROW, QD] = a
+    B[QD, ROW] = b
     P = A @ B
     out = c.copy()
-    for l in range(32):
-        out[l, 0] += P[l >> 2, 2 * (l & 3)]
-        out[l, 1] += P[l >> 2, 2 * (l & 3) + 1]
+    out[:, 0] += P[ROW, 2 * QD]
+    out[:, 1] += P[ROW, 2 * QD + 1]
     return out
 
 
-@pytest.mark.parametrize("nb", [5, 6, 11, 40])
+def factor_fraction_free(frag, rng):
+    """`factor_fraction_free` of the header: fraction-free elimination of [C | 1], every lane two entries of each."""
+    c = frag.copy()
+    i, j0 = ROW, 2 * QD
+    b = np.stack([(j0 == i) * 1.0, (j0 + 1 == i) * 1.0], axis=1)
+    Q, sx, sy, si = 1.0, np.zeros(32), np.zeros(32), np.zeros(32)
+    for k in range(8):
+        ck = c[:, k & 1]
+        ckk = ck[4 * k + (k >> 1)]
+        cik, cj0, cj1 = ck[4 * i + (k >> 1)], ck[4 * j0 + (k >> 1)], ck[4 * (j0 + 1) + (k >> 1)]
+        bk0, bk1 = b[4 * k + QD, 0], b[4 * k + QD, 1]
+        alpha = (1.0 / ckk) * (1.0 + 2.0 ** -20 * rng.uniform(-1, 1))       # rcp.approx: ~20 good bits
+        sigma = 1.0 / np.sqrt(Q * ckk)
+        sx, sy, si = np.where(j0 == k, sigma, sx), np.where(j0 + 1 == k, sigma, sy), np.where(i == k, sigma, si)
+        c[:, 0] = np.where((i > k) & (j0 > k), (ckk * c[:, 0] - cik * cj0) * alpha, c[:, 0])
+        c[:, 1] = np.where((i > k) & (j0 + 1 > k), (ckk * c[:, 1] - cik * cj1) * alpha, c[:, 1])
+        b[:, 0] = np.where(i > k, (ckk * b[:, 0] - cik * bk0) * alpha, b[:, 0])
+        b[:, 1] = np.where(i > k, (ckk * b[:, 1] - cik * bk1) * alpha, b[:, 1])
+        Q *= ckk * alpha
+    L = np.stack([np.where(j0 <= i, c[:, 0] * sx, 0.0), np.where(j0 + 1 <= i, c[:, 1] * sy, 0.0)], axis=1)
+    W = np.stack([np.where(j0 <= i, b[:, 0] * si, 0.0), np.where(j0 + 1 <= i, b[:, 1] * si, 0.0)], axis=1)
+    return L, W
+
+
+def slots_of(b, NT):
+    """Bulk warp b: slot s -> (I, J) or None, as the RT_IN_HI / RT_SLOT_J / RT_SLOT_OK macros of the header."""
+    hi, lo = NT - 1 - b, b + 1
+    out = []
+    for s in range(NT):
+        in_hi = s < hi
+        ok = in_hi or lo < hi
+        out.append(((hi if in_hi else lo), (s if in_hi else NT - 1 - s)) if ok else None)
+    return hi, lo, out
+
+
+@pytest.mark.parametrize("NT", list(range(2, 17)))
+def test_tile_ownership(NT):
+    """Every off-diagonal tile of the lower block triangle is owned by exactly one slot of one bulk warp, a slot's column
+    is one of two compile-time values, and the active slots of a panel form the contiguous range the chunk skipping of
+    the trailing update assumes."""
+    nbw = max(1, NT // 2)
+    seen = []
+    for b in range(nbw):
+        hi, lo, sl = slots_of(b, NT)
+        for s, t in enumerate(sl):
+            if t is not None:
+                I, J = t
+                assert 0 <= J < I < NT and J in (s, NT - 1 - s)
+                seen.append(t)
+        for p in range(NT - 1):
+            active = [s for s, t in enumerate(sl) if t is not None and t[1] > p]
+            top = max(hi, NT - 1 - p)
+            assert all(p < s < top for s in active)
+            # every valid slot inside the range is active (invalid ones multiply by zero)
+            assert active == [s for s in range(p + 1, top) if sl[s] is not None]
+            solved = [t for t in sl if t is not None and t[1] == p]
+            assert sorted(I for I, _ in solved) == sorted(([hi] if hi > p else []) + ([lo] if p < lo < hi else []))
+    assert sorted(seen) == [(I, J) for I in range(NT) for J in range(I)]
+
+
+@pytest.mark.parametrize("nb", [5, 6, 11, 40, 42])
 def test_register_tiled_cholesky_data_flow(nb):
     rng = np.random.default_rng(nb)
     n3, NP = 3 * nb, -(-3 * nb // 8) * 8
     NT = NP // 8
-    ntiles = NT * (NT + 1) // 2
-    tpw = (ntiles + 3) // 4
+    NOFF = NT * (NT - 1) // 2
+    nbw = max(1, NT // 2)
     a = 0.05
     k = 2 * np.pi * np.arange(nb) / nb
     loc = 0.3 * np.stack([np.cos(k), np.sin(k), 0.2 * np.sin(2 * k)], 1) + 0.01 * rng.standard_normal((nb, 3))
@@ -42,9 +107,11 @@ def test_register_tiled_cholesky_data_flow(nb):
     xi[:n3] = rng.standard_normal(n3)
     mu_self = 1.0 / (6 * np.pi * a)
 
-    # pair table (ci, cr / r^2), q = i (i - 1) / 2 + j
-    PT = np.zeros((nb * (nb - 1) // 2, 2))
-    for q in range(len(PT)):
+    # value table: [0, 1, mu_self, -] then 6 entries per bead pair q = i (i - 1) / 2 + j, from `rpy_pair` (one reciprocal
+    # square root, no division)
+    val = np.zeros(4 + 6 * (nb * (nb - 1) // 2))
+    val[1], val[2] = 1.0, mu_self
+    for q in range(nb * (nb - 1) // 2):
         i = int((np.sqrt(np.float32(8.0 * q + 1.0)) + 1.0) * 0.5)
         while i * (i - 1) // 2 > q:
             i -= 1
@@ -54,173 +121,16 @@ def test_register_tiled_cholesky_data_flow(nb):
         assert 0 <= j < i < nb
         d = loc[i] - loc[j]
         r2 = d @ d
-        rr = np.sqrt(r2)
-        if rr > 2 * a:
-            pref = 1 / (8 * np.pi * rr)
-            ci, cr = pref * (1 + 2 * a * a / (3 * r2)), pref * (1 - 2 * a * a / r2)
+        inv_r = 1 / np.sqrt(r2)
+        if r2 > 4 * a * a:
+            pref = inv_r * (0.125 / np.pi)
+            ci, crp = pref * (1 + (2 * a * a / 3) * inv_r ** 2), pref * (1 - 2 * a * a * inv_r ** 2) * inv_r ** 2
         else:
-            qq = 1 / (6 * np.pi * a * a) / (32 * r2 * rr)
-            ci, cr = qq * (16 * r2 * rr * 2 * a - 9 * r2 * r2), qq * 3 * r2 * r2
-        PT[q] = ci, cr / r2
+            ci, crp = (mu_self / a) * (a - (9 / 32) * r2 * inv_r), (mu_self / a) * (3 / 32) * inv_r
+        val[4 + 6 * q:10 + 6 * q] = [crp * d[0] * d[0] + ci, crp * d[0] * d[1], crp * d[0] * d[2],
+                                     crp * d[1] * d[1] + ci, crp * d[1] * d[2], crp * d[2] * d[2] + ci]
 
-    def entry(R, C):
-        if R >= n3 or C >= n3:
-            return 1.0 if R == C else 0.0
-        bi, al, bj, be = R // 3, R % 3, C // 3, C % 3
-        if bi == bj:
-            return mu_self if al == be else 0.0
-        hi, lo = max(bi, bj), min(bi, bj)
-        ci, crp = PT[hi * (hi - 1) // 2 + lo]
-        return crp * (pos[3 * bi + al] - pos[3 * bj + al]) * (pos[3 * bi + be] - pos[3 * bj + be]) + (ci if al == be else 0.0)
-
-    mu_ref = np.asarray(rpy.muTT_numpy(loc, np.full(nb, a)))
-    mu_model = np.array([[entry(R, C) for C in range(n3)] for R in range(n3)])
-    assert np.allclose(mu_model, mu_ref, rtol=1e-12, atol=1e-14)
-
-    # tile map
-    tmap = []
-    for s in range(ntiles):
-        J, rem = 0, s
-        while rem >= NT - J:
-            rem -= NT - J
-            J += 1
-        tmap.append((J + rem, J))
-    assert sorted(tmap) == sorted((I, J) for J in range(NT) for I in range(J, NT)) and tmap[:NT] == [(I, 0) for I in range(NT)]
-
-    lanes = np.arange(32)
-    acc = np.zeros((4, tpw, 32, 2))
-    for w in range(4):
-        for kk in range(tpw):
-            sl = w + 4 * kk
-            if sl < ntiles:
-                I, J = tmap[sl]
-                for l in lanes:
-                    R, C = 8 * I + (l >> 2), 8 * J + 2 * (l & 3)
-                    acc[w, kk, l] = entry(R, C), entry(R, C + 1)
-    Raw = np.zeros(NT * 80)
-    Pan = np.full(NT * 64, np.nan)
-    y = np.zeros(128)
-
-    def store_raw(I, frag):
-        for l in lanes:
-            o = I * 80 + (l >> 2) * 10 + 2 * (l & 3)
-            Raw[o:o + 2] = frag[l]
-    for w in range(4):
-        for kk in range(tpw):
-            if w + 4 * kk < NT:
-                store_raw(w + 4 * kk, acc[w, kk])
-    for p in range(NT):
-        row0 = 8 * p
-        D = np.array([[Raw[p * 80 + i * 10 + j] if j <= i else 0.0 for j in range(8)] for i in range(8)])
-        dinv = np.zeros(8)
-        for kq in range(8):
-            dinv[kq] = 1 / np.sqrt(D[kq, kq])
-            D[kq:, kq] *= dinv[kq]
-            for j in range(kq + 1, 8):
-                D[j:, j] -= D[j:, kq] * D[j, kq]
-        for tid in range(row0, NP):
-            I, r = tid >> 3, tid & 7
-            if I == p:
-                v = D[r].copy()
-            else:
-                v = Raw[I * 80 + r * 10: I * 80 + r * 10 + 8].copy()
-                for kq in range(8):
-                    v[kq] *= dinv[kq]
-                    v[kq + 1:] -= v[kq] * D[kq + 1:, kq]
-            y[tid] += v @ xi[row0:row0 + 8]
-            if I > p:
-                dst = I * 64 + r * 4
-                Pan[dst:dst + 4] = v[:4]
-                Pan[dst + 32:dst + 36] = v[4:]
-        for w in range(4):
-            for kk in range(tpw):
-                sl = w + 4 * kk
-                if sl < ntiles:
-                    I, J = tmap[sl]
-                    if J > p:
-                        for h in range(2):
-                            acc[w, kk] = dmma884(acc[w, kk], -Pan[I * 64 + 32 * h + lanes], Pan[J * 64 + 32 * h + lanes])
-                        if J == p + 1:
-                            store_raw(I, acc[w, kk])
-    L = np.linalg.cholesky(mu_ref)
-    assert np.allclose(y[:n3], L @ xi[:n3], rtol=1e-10, atol=1e-12)
-
-    # drift from the pair table, thread (i, chunk)
-    part = np.zeros((3, NP))
-    for tid in range(3 * nb):
-        i, chunk = tid % nb, tid // nb
-        o = mu_self * frc[3 * i:3 * i + 3] if chunk == 0 else np.zeros(3)
-        for j in range(chunk, nb, 3):
-            if j == i:
-                continue
-            hi, lo = max(i, j), min(i, j)
-            ci, crp = PT[hi * (hi - 1) // 2 + lo]
-            d = loc[i] - loc[j]
-            o = o + crp * (d @ frc[3 * j:3 * j + 3]) * d + ci * frc[3 * j:3 * j + 3]
-        part[chunk, 3 * i:3 * i + 3] = o
-    assert np.allclose(part.sum(0)[:n3], mu_ref @ frc, rtol=1e-11, atol=1e-13)
-
-
-def test_shared_memory_size_formula_matches_the_header():
-    from stochastic_b200.sde_solver import bead_regtile_smem_bytes
-    # RT_OFF_* of csrc/sde_bead_kernel.cuh for N = 40: 6 NP + value table (4 + 6 NPAIR) + 80 NT + 64 NT + 72
-    # + tile maps (3 x 36 bytes); three CTAs of the 192-thread variant fit the 227 KB of an SM
-    assert bead_regtile_smem_bytes(40) == 8 * (720 + 4684 + 1200 + 960 + 72 + 14)
-    assert bead_regtile_smem_bytes(5) == 8 * (96 + 64 + 160 + 128 + 72 + 3)
-    assert 3 * (bead_regtile_smem_bytes(40, 192) + 1024) <= 227 * 1024
-
-
-@pytest.mark.parametrize("nbw", [3, 4, 5, 6, 7])
-@pytest.mark.parametrize("nb", [5, 6, 11, 40, 42])
-def test_bulk_warp_tile_maps(nb, nbw):
-    """The packed tile maps of the bulk warps (sde_bead_kernel: `map[q]`): every off-diagonal tile exactly once, dealt
-    round-robin in column-major order, so that for each warp the column index never decreases along its slots - the
-    property the chunk-wise skipping of finished tiles relies on - and unused slots are (0, 0)."""
-    NT = -(-3 * nb // 8)
-    noff = NT * (NT - 1) // 2
-    opw = -(-noff // nbw)
-    mapw = (-(-opw // 5) * 5 + 3) // 4
-    seen = []
-    for w in range(nbw):
-        last_j = 0
-        slots = []
-        for k in range(mapw * 4):
-            o = w + nbw * k
-            v = 0
-            if k < opw and o < noff:
-                J, rem = 0, o
-                while rem >= NT - 1 - J:
-                    rem -= NT - 1 - J
-                    J += 1
-                v = (J + 1 + rem) | (J << 4)
-            I, J = v & 15, v >> 4
-            slots.append((I, J, bool(v)))
-            if v:
-                assert NT > I > J >= last_j
-                last_j = J
-                seen.append((I, J))
-            else:
-                assert (I, J) == (0, 0)
-        # the chunk-activity test of the trailing update (`jlast`): for every panel p a chunk is entered iff it
-        # holds an active tile
-        for p in range(NT):
-            for ch in range(-(-opw // 5)):
-                last = min(ch * 5 + 4, opw - 1)
-                jlast = slots[last][1] if (w + nbw * last < noff or last == 0) else slots[max(last - 1, 0)][1]
-                truth = any(valid and J > p for (I, J, valid) in slots[ch * 5:ch * 5 + 5])
-                assert (jlast > p) == truth, (nb, nbw, w, p, ch)
-    assert sorted(seen) == sorted((I, J) for J in range(NT) for I in range(J + 1, NT))
-
-
-def test_value_table_indices_and_lane_parallel_factorisation():
-    """`mobility_index` (symmetric 3x3 pair blocks in a value table) and the lane-parallel Cholesky of the diagonal
-    block on its accumulator fragment (`factor_diagonal`), modelled lane by lane with explicit shuffles."""
-    nb, n3 = 7, 21
-    rng = np.random.default_rng(1)
-    blocks = rng.standard_normal((nb * (nb - 1) // 2, 6))
-    val = np.concatenate([[0.0, 1.0, 0.25, 0.0], blocks.ravel()])
-
-    def index(R, C):
+    def mobility_index(R, C):
         if R >= n3 or C >= n3:
             return 1 if R == C else 0
         bi, al, bj, be = R // 3, R % 3, C // 3, C % 3
@@ -229,40 +139,106 @@ def test_value_table_indices_and_lane_parallel_factorisation():
         hi, lo = max(bi, bj), min(bi, bj)
         a0, a1 = min(al, be), max(al, be)
         return 4 + 6 * (hi * (hi - 1) // 2 + lo) + (a1 if a0 == 0 else a0 + a1 + 1)
-    sym = {(0, 0): 0, (0, 1): 1, (0, 2): 2, (1, 1): 3, (1, 2): 4, (2, 2): 5}
-    M = np.array([[val[index(R, C)] for C in range(24)] for R in range(24)])
-    assert np.allclose(M, M.T) and np.allclose(M[21:, 21:], np.eye(3)) and np.all(M[21:, :21] == 0)
-    for bi in range(nb):
-        for bj in range(bi):
-            blk = np.array([[blocks[bi * (bi - 1) // 2 + bj][sym[min(a, b), max(a, b)]] for b in range(3)] for a in range(3)])
-            assert np.array_equal(M[3 * bi:3 * bi + 3, 3 * bj:3 * bj + 3], blk)
-        assert np.array_equal(M[3 * bi:3 * bi + 3, 3 * bi:3 * bi + 3], 0.25 * np.eye(3))
 
-    # lane-parallel factorisation
-    B = rng.standard_normal((8, 8))
-    S = B @ B.T + 8 * np.eye(8)
-    c = np.array([[S[l >> 2, 2 * (l & 3)], S[l >> 2, 2 * (l & 3) + 1]] for l in range(32)])
-    lanes = np.arange(32)
-    i, jp = lanes >> 2, lanes & 3
-    j0 = 2 * jp
-    rinvs = np.zeros(8)
-    for k in range(8):
-        comp = k & 1
-        d = c[4 * k + (k >> 1), comp]
-        rinv = 1 / np.sqrt(d)
-        rinvs[k] = rinv
-        c[jp == (k >> 1), comp] *= rinv
-        if k < 7:
-            src = c[:, comp].copy()
-            lik = src[4 * i + (k >> 1)]
-            lj0 = src[np.minimum(4 * j0 + (k >> 1), 31)]
-            lj1 = src[np.minimum(4 * (j0 + 1) + (k >> 1), 31)]
-            m0, m1 = j0 > k, j0 + 1 > k
-            c[m0, 0] -= (lik * lj0)[m0]
-            c[m1, 1] -= (lik * lj1)[m1]
-    Lm = np.zeros((8, 8))
-    for l in range(32):
-        Lm[i[l], j0[l]] = c[l, 0] if j0[l] <= i[l] else 0.0
-        Lm[i[l], j0[l] + 1] = c[l, 1] if j0[l] + 1 <= i[l] else 0.0
-    assert np.allclose(Lm, np.linalg.cholesky(S), rtol=1e-12, atol=1e-13)
-    assert np.allclose(rinvs, 1 / np.diag(Lm))
+    mu_ref = np.asarray(rpy.muTT_numpy(loc, np.full(nb, a)))
+    mu_model = np.array([[val[mobility_index(R, C)] for C in range(n3)] for R in range(n3)])
+    assert np.allclose(mu_model, mu_ref, rtol=1e-12, atol=1e-14)
+
+    def fragment(I, J):
+        return np.array([[val[mobility_index(8 * I + (l >> 2), 8 * J + 2 * (l & 3) + e)] for e in (0, 1)] for l in LANES])
+
+    # meta numbering of the header: off-diagonal tile (I, J) is I (I - 1) / 2 + J, diagonal tile k is NOFF + k
+    assert sorted(I * (I - 1) // 2 + J for I in range(NT) for J in range(I)) == list(range(NOFF))
+
+    bulk = []
+    for b in range(nbw):
+        hi, lo, sl = slots_of(b, NT)
+        bulk.append(dict(hi=hi, lo=lo, slots=sl, acc=[fragment(*t) if t is not None else np.zeros((32, 2)) for t in sl],
+                         dgh=fragment(hi, hi), dgl=fragment(lo, lo), yph=np.zeros(32), ypl=np.zeros(32),
+                         nah=np.zeros((32, 2)), nal=np.zeros((32, 2))))
+    Pan = np.zeros((NT, 64))
+    Linv, nextd = np.zeros(64), np.zeros(64)
+    yd4, yb = np.zeros(4 * NP), np.zeros(NP)
+    cur = fragment(0, 0)
+    for p in range(NT):
+        # chain warp: factor, publish the inverse, the diagonal rows' terms of y (four partial sums per row)
+        L, W = factor_fraction_free(cur, rng)
+        Linv[OFF], Linv[OFF + 1] = W[:, 0], W[:, 1]
+        yd4[4 * 8 * p + LANES] = L[:, 0] * xi[8 * p + 2 * QD] + L[:, 1] * xi[8 * p + 2 * QD + 1]
+        if p + 1 == NT:
+            break
+        # ---- barrier 1 ----
+        lf = Linv[OFF], Linv[OFF + 1]
+        x2 = xi[8 * p + 2 * QD], xi[8 * p + 2 * QD + 1]
+        for w in bulk:
+            # `solve_column<P>`: slot P of the hi row, slot NT-1-P of the lo row
+            todo = []
+            if p < w["hi"]:
+                todo.append((p, w["hi"], "h"))
+            if w["lo"] < w["hi"] and NT - 1 - p >= w["hi"]:
+                todo.append((NT - 1 - p, w["lo"], "l"))
+            for s, I, tag in todo:
+                assert w["slots"][s] == (I, p)
+                out = dmma884(dmma884(np.zeros((32, 2)), w["acc"][s][:, 0], lf[0]), w["acc"][s][:, 1], lf[1])
+                Pan[I, OFF], Pan[I, OFF + 1] = out[:, 0], out[:, 1]
+                w["na" + tag] = -out
+                w["dg" + tag] = dmma884(dmma884(w["dg" + tag], -out[:, 0], out[:, 0]), -out[:, 1], out[:, 1])
+                if I == p + 1:
+                    nextd[OFF], nextd[OFF + 1] = w["dg" + tag][:, 0], w["dg" + tag][:, 1]
+                w["yp" + tag] += out[:, 0] * x2[0] + out[:, 1] * x2[1]
+        # ---- barrier 2 ----
+        cur = np.stack([nextd[OFF], nextd[OFF + 1]], axis=1)
+        for w in bulk:
+            top = max(w["hi"], NT - 1 - p)
+            for c0 in range(0, NT, 5):
+                if c0 + 4 > p and c0 < top:
+                    for s in range(c0, min(c0 + 5, NT)):
+                        in_hi = s < w["hi"]
+                        J = s if in_hi else NT - 1 - s
+                        on = w["slots"][s] is not None and J > p
+                        na = (w["nah"] if in_hi else w["nal"]) * (1.0 if on else 0.0)
+                        w["acc"][s] = dmma884(dmma884(w["acc"][s], na[:, 0], Pan[J, OFF]), na[:, 1], Pan[J, OFF + 1])
+    for w in bulk:
+        for name, I in (("yph", w["hi"]), ("ypl", w["lo"])):
+            if name == "ypl" and not w["lo"] < w["hi"]:
+                continue
+            v = w[name] + w[name][LANES ^ 1]
+            v = v + v[LANES ^ 2]
+            yb[8 * I + ROW[QD == 0]] = v[QD == 0]
+    Lref = np.linalg.cholesky(mu_ref)
+    yd = yd4.reshape(NP, 4).sum(1)
+    assert np.allclose((yb + yd)[:n3], Lref @ xi[:n3], rtol=1e-10, atol=1e-12)
+
+    # drift from the pair table, thread (i, chunk); the pair {i, i} reads another pair's block times zero
+    from stochastic_b200.sde_solver import bead_regtile_block
+    dch = max(3, min(6, bead_regtile_block(nb) // nb))
+    part = np.zeros((dch, NP))
+    for tid in range(dch * nb):
+        i, chunk = tid % nb, tid // nb
+        o = mu_self * frc[3 * i:3 * i + 3] if chunk == 0 else np.zeros(3)
+        for j in range(chunk, nb, dch):
+            jj = (1 if i == 0 else 0) if j == i else j
+            on = 0.0 if j == i else 1.0
+            hi, lo = max(i, jj), min(i, jj)
+            blk = val[4 + 6 * (hi * (hi - 1) // 2 + lo):][:6]
+            B = np.array([[blk[0], blk[1], blk[2]], [blk[1], blk[3], blk[4]], [blk[2], blk[4], blk[5]]])
+            o = o + B @ (on * frc[3 * j:3 * j + 3])
+        part[chunk, 3 * i:3 * i + 3] = o
+    assert np.allclose(part.sum(0)[:n3], mu_ref @ frc, rtol=1e-11, atol=1e-13)
+
+
+def test_shared_memory_size_and_block_formulas_match_the_header():
+    from stochastic_b200.sde_solver import bead_regtile_block, bead_regtile_smem_bytes
+    # (8 + drift chunks) NP + value table + overlap coefficients + 2 NT tiles + inverse block + next diagonal tile
+    assert bead_regtile_smem_bytes(40) == 8 * (14 * 120 + 4684 + 780 + 1920 + 128)
+    assert bead_regtile_smem_bytes(5) == 8 * (14 * 16 + 64 + 10 + 256 + 128)
+    assert bead_regtile_block(40) == 256 and bead_regtile_block(42) == 288 and bead_regtile_block(5) == 64
+    assert 2 * (bead_regtile_smem_bytes(40) + 1024) <= 227 * 1024
+    import os
+    import stochastic_b200
+    header = open(os.path.join(os.path.dirname(stochastic_b200.__file__), "csrc", "sde_bead_kernel.cuh")).read()
+    # the carve-up the formula mirrors
+    for piece in ("RT_OFF_PART + RT_DCH * SDE_NP", "RT_OFF_YD + 4 * SDE_NP", "RT_OFF_VAL + RT_NVAL",
+                  "RT_OFF_OVL + RT_NPAIR + (RT_NPAIR & 1)", "RT_OFF_PAN + 2 * RT_NT * 64", "RT_OFF_LINV + 64", "RT_OFF_NEXTD + 64"):
+        assert piece in header, piece
+    assert re.search(r"SDE_BLOCK == 32 \* \(1 \+ RT_NBW\)", header)

@@ -32,11 +32,15 @@ def test_bead_kernel_equals_generic_traced_kernel(dtype, tol):
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
     a = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
     solver.use_bead_kernel = True
-    b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
-    for k in ("time_values", "solution_values", "wiener_values"):
-        x, y = np.asarray(a[k]), np.asarray(b[k])
-        assert x.shape == y.shape and x.dtype == dtype
-        assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
+    for regtile in ((None, False) if f64 else (None,)):       # fp64: the register-tiled kernel (default) and the shared-memory one
+        solver.bead_regtile = regtile
+        b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
+        assert f"SDE_BEAD_REGTILE {1 if f64 and regtile is None else 0}" in solver._bead_plan(
+            workloads.dna_loop(**kw), f64, "original").ks.source
+        for k in ("time_values", "solution_values", "wiener_values"):
+            x, y = np.asarray(a[k]), np.asarray(b[k])
+            assert x.shape == y.shape and x.dtype == dtype
+            assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, regtile, np.abs(x - y).max())
 
 
 def test_bead_kernel_rejects_other_schemes_and_shards():
@@ -107,17 +111,18 @@ def test_twisted_ring_bead_kernel_equals_generic_traced_kernel(dtype, tol):
 @pytest.mark.parametrize("twist", [False, True])
 def test_register_tiled_and_shared_memory_variants_agree(twist):
     """fp64, 40 beads: the register-tiled kernel (mobility and Cholesky factor in tensor-core accumulator fragments,
-    drift from the pair table, noise folded into the panel solves) against the shared-memory variant."""
+    fraction-free factorisation of the diagonal tiles, row solves as tensor-core products, drift from the pair table,
+    noise folded into the row solves) against the shared-memory variant."""
     prob = workloads.dna_loop(n_beads=40, tmax=1.2e-6, f64=True, twist=twist, x0=writhed_ring(40))
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    solver.bead_regtile = False
     b = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
     assert "SDE_BEAD_REGTILE 0" in solver._bead_plan(prob, True, "original").ks.source
     solver.bead_regtile = True
-    for block in (None, 128, 256):             # default (160 threads, three CTAs per SM) and the two-CTA variants
-        solver.block_size = block
-        a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
-        assert "SDE_BEAD_REGTILE 1" in solver._bead_plan(prob, True, "original").ks.source
-        for k in ("time_values", "solution_values", "wiener_values"):
-            x, y = np.asarray(a[k]), np.asarray(b[k])
-            assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
-            assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, block, np.abs(x - y).max())
+    a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
+    plan = solver._bead_plan(prob, True, "original")
+    assert "SDE_BEAD_REGTILE 1" in plan.ks.source and plan.ks.block == 256      # chain warp + 7 bulk warps
+    for k in ("time_values", "solution_values", "wiener_values"):
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
+        assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())

@@ -197,3 +197,61 @@ def test_both_stepping_kernels_agree_bit_for_bit():
         out.append(solver.solve_many(prob, n_trajectories=777, seed=5, chunk_size=4, chunks_per_randomization=2))
     for k in ("time_values", "solution_values", "wiener_values"):
         assert np.array_equal(np.asarray(out[0][k]), np.asarray(out[1][k]))
+
+
+def _stores_three_ways(prob, scheme, dt, n_traj, tma_choices, **kw):
+    """The same run with snapshots stored (a) by the TMA unit, (b) by the transposed write-out loop, (c) directly."""
+    out = []
+    for choice in list(tma_choices) + ["loop", "direct"]:
+        solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
+        solver.warp_specialize = kw.get("warp_specialize")
+        old = pychastic.config.get("snapshot_tma")
+        try:
+            if choice == "loop":
+                pychastic.config.update("snapshot_tma", False)
+            elif choice == "direct":
+                pychastic.config.update("snapshot_tma", False)
+                solver.snap_tile = 1
+            elif choice != "auto":
+                solver.snap_tile = choice
+            args = {k: v for k, v in kw.items() if k != "warp_specialize"}
+            out.append((choice, solver.solve_many(prob, n_trajectories=n_traj, seed=4, **args)))
+        finally:
+            pychastic.config.update("snapshot_tma", old)
+    ref = out[-1][1]
+    for choice, sol in out[:-1]:
+        for k in ("time_values", "solution_values", "wiener_values"):
+            assert np.array_equal(np.asarray(sol[k]), np.asarray(ref[k])), (choice, k)
+    return ref
+
+
+@pytest.mark.parametrize("n_traj,steps", [(45, 24), (33, 38), (1, 16), (70, 6), (64, 40), (300, 130), (129, 37)])
+def test_tma_snapshot_tiles_equal_plain_stores_scalar_f64(n_traj, steps):
+    """Snapshot tiles handed to the TMA unit (csrc/sde_snap_tma.cuh), every row length and swizzle pattern, against the
+    write-out loop and the direct stores, bit for bit: ragged trajectory counts (rows past the end are clipped by the
+    tensor map), runs that end inside a tile, an odd snapshot count (rows no tensor map can describe: falls back)."""
+    prob, _ = P.gbm(0.2, 0.5, 1.0, 1.0)
+    P.as_f64(prob)
+    choices = ["auto"]
+    if steps % 2 == 0:
+        choices += [("tma", 16, 3), ("tma", 8, 2), ("tma", 4, 1), ("tma", 2, 0)]
+    _stores_three_ways(prob, "euler", 1.0 / steps, n_traj, choices)
+
+
+@pytest.mark.parametrize("scheme,ws", [("milstein", None), ("wagner_platen", False), ("wagner_platen", True)])
+def test_tma_snapshot_tiles_equal_plain_stores_vector_state(scheme, ws):
+    """d = m = 2: the tile of a field of width 2 is two boxes; also the consumers of the warp-specialised kernel."""
+    prob, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    P.as_f64(prob)
+    # (the ring of the warp-specialised kernel leaves room for 16-byte rows only; the single-role Wagner-Platen kernel
+    # stages 94 KB of normals per 256-thread CTA, which rules out 128-byte rows)
+    choices = ["auto", ("tma", 2, 0)] + ([] if ws else [("tma", 8, 2), ("tma", 4, 1)]) + ([("tma", 16, 3)] if ws is None else [])
+    _stores_three_ways(prob, scheme, 1.0 / 44, 200, choices, warp_specialize=ws)
+    _stores_three_ways(prob, scheme, 1.0 / 64, 131, choices, warp_specialize=ws, chunk_size=2, chunks_per_randomization=4)
+
+
+def test_tma_snapshot_tiles_equal_plain_stores_f32():
+    prob, _ = P.gbm(0.2, 0.5, 1.0, 1.0)
+    _stores_three_ways(prob, "euler", 1.0 / 72, 77, ["auto", ("tma", 32, 3), ("tma", 16, 2), ("tma", 8, 1), ("tma", 4, 0)])
+    prob, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    _stores_three_ways(prob, "euler", 1.0 / 36, 50, ["auto", ("tma", 32, 3), ("tma", 4, 0)])
