@@ -87,7 +87,8 @@ typedef struct sdeb200_bead_args {
     double twist_k;          /* twisting stiffness x (2 pi)^2: U_twist = twist_k / 2 (Lk - Wr)^2 (ignored without SDE_BEAD_TWIST) */
     double linking_number;   /* Lk */
     void* workspace;         /* device scratch of the register-tiled variant (SDE_BEAD_REGTILE): 128 bytes per 8x8 tile of
-                                the lower block triangle, written and read by the kernel itself; NULL otherwise */
+                                the lower block triangle (written and read by the kernel itself), followed by 1024
+                                uint32 CTA arrival counters that the caller zeroes before every launch; NULL otherwise */
     void* out_t;             /* device (traj_count, n_snapshots)      or NULL */
     void* out_x;             /* device (traj_count, n_snapshots, 3N)  or NULL */
     void* out_w;             /* device (traj_count, n_snapshots, 3N)  or NULL */

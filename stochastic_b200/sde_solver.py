@@ -332,6 +332,7 @@ def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
         f"#define SDE_BEAD_CHAIN_PER_THREAD {int(os.environ.get('SDEB200_BEAD_CHAIN_PER_THREAD', '0'))}",
         f"#define SDE_BEAD_TIMING {int(os.environ.get('SDEB200_BEAD_TIMING', '0'))}",   # diagnostics: per-phase cycle counts
         *([f"#define SDE_BEAD_EXPERIMENT_SKIP {int(os.environ['SDEB200_BEAD_SKIP'])}"] if os.environ.get("SDEB200_BEAD_SKIP") else []),
+        *([f"#define SDE_BEAD_UPD_GROUP {int(os.environ['SDEB200_BEAD_UPD_GROUP'])}"] if os.environ.get("SDEB200_BEAD_UPD_GROUP") else []),
         '#include "sde_bead_kernel.cuh"', ""])
 
 
@@ -646,7 +647,8 @@ class SDESolver:
             smem = bead_regtile_smem_bytes(nb)
             ctas_per_sm = max(1, min(2 if block > 170 else 3, (227 * 1024) // (smem + 1024)))
             npad = -(-d // 8) * 8
-            workspace = torch.empty(((npad // 8) * (npad // 8 + 1) // 2) * 32, dtype=torch.int32, device=dev)
+            # value-table indices of every (tile, lane), then 1024 CTA arrival counters per SM (must be zero)
+            workspace = torch.zeros(((npad // 8) * (npad // 8 + 1) // 2) * 32 + 1024, dtype=torch.int32, device=dev)
             args.workspace = workspace.data_ptr()
         else:
             npad = -(-d // 8) * 8                  # must match SDE_NP / SDE_LSIZE in csrc/sde_bead_kernel.cuh
