@@ -109,6 +109,88 @@ __device__ __forceinline__ void factor<4>(double cx, double cy, const int lane, 
     wy = (j0 + 1 <= i) ? by * si : 0.0;
 }
 
+// pivot row through shared memory instead of shuffles: the four lanes of row k publish their entries of both fragments,
+// every lane reads c_kk, c_ik = c_ki (symmetry), its two columns of row k of C and of B: 2 STS + 4 LDS per pivot instead
+// of 12 SHFL and the register moves that pair their 32-bit halves
+template <>
+__device__ __forceinline__ void factor<5>(double cx, double cy, const int lane, double& lx, double& ly, double& wx, double& wy) {
+    __shared__ __align__(16) double rowbuf[2][16];
+    const int i = lane >> 2, qd = lane & 3, j0 = 2 * qd;
+    double bx = (j0 == i) ? 1.0 : 0.0, by = (j0 + 1 == i) ? 1.0 : 0.0;
+    double Q = 1.0, px = 1.0, py = 1.0, pi = 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double* rb = rowbuf[k & 1];
+        if (i == k) {
+            *reinterpret_cast<double2*>(rb + j0) = make_double2(cx, cy);
+            *reinterpret_cast<double2*>(rb + 8 + j0) = make_double2(bx, by);
+        }
+        __syncwarp();
+        const double ckk = rb[k], cik = rb[i];
+        const double2 cj = *reinterpret_cast<const double2*>(rb + j0), bk = *reinterpret_cast<const double2*>(rb + 8 + j0);
+        double alpha;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(alpha) : "d"(ckk));
+        const double pq = Q * ckk;
+        px = (j0 == k) ? pq : px;
+        py = (j0 + 1 == k) ? pq : py;
+        pi = (i == k) ? pq : pi;
+        const double nx = fma(ckk, cx, -(cik * cj.x)) * alpha, ny = fma(ckk, cy, -(cik * cj.y)) * alpha;
+        const double nbx = fma(ckk, bx, -(cik * bk.x)) * alpha, nby = fma(ckk, by, -(cik * bk.y)) * alpha;
+        const bool below = i > k;
+        cx = (below && j0 > k) ? nx : cx;
+        cy = (below && j0 + 1 > k) ? ny : cy;
+        bx = below ? nbx : bx;
+        by = below ? nby : by;
+        Q *= ckk * alpha;
+    }
+    const double sx = pivot_rsqrt(px), sy = pivot_rsqrt(py), si = pivot_rsqrt(pi);
+    lx = (j0 <= i) ? cx * sx : 0.0;
+    ly = (j0 + 1 <= i) ? cy * sy : 0.0;
+    wx = (j0 <= i) ? bx * si : 0.0;
+    wy = (j0 + 1 <= i) ? by * si : 0.0;
+}
+
+// variant 5 + power-of-two scale from the exponent bits folded into the two row factors + one reciprocal square root per
+// lane, exchanged through shared memory
+template <>
+__device__ __forceinline__ void factor<6>(double cx, double cy, const int lane, double& lx, double& ly, double& wx, double& wy) {
+    __shared__ __align__(16) double rowbuf[2][16];
+    __shared__ __align__(16) double sig[8];
+    const int i = lane >> 2, qd = lane & 3, j0 = 2 * qd;
+    double bx = (j0 == i) ? 1.0 : 0.0, by = (j0 + 1 == i) ? 1.0 : 0.0;
+    double Q = 1.0, mypq = 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double* rb = rowbuf[k & 1];
+        if (i == k) {
+            *reinterpret_cast<double2*>(rb + j0) = make_double2(cx, cy);
+            *reinterpret_cast<double2*>(rb + 8 + j0) = make_double2(bx, by);
+        }
+        __syncwarp();
+        const double ckk = rb[k], cik = rb[i];
+        const double2 cj = *reinterpret_cast<const double2*>(rb + j0), bk = *reinterpret_cast<const double2*>(rb + 8 + j0);
+        const double alpha = __hiloint2double(0x7fe00000 - (__double2hiint(ckk) & 0x7ff00000), 0);   // 2^-e: exact products
+        mypq = (lane == k) ? Q * ckk : mypq;
+        const double g = ckk * alpha, nh = -(cik * alpha);
+        const double nx = fma(g, cx, nh * cj.x), ny = fma(g, cy, nh * cj.y);
+        const double nbx = fma(g, bx, nh * bk.x), nby = fma(g, by, nh * bk.y);
+        const bool below = i > k;
+        cx = (below && j0 > k) ? nx : cx;
+        cy = (below && j0 + 1 > k) ? ny : cy;
+        bx = below ? nbx : bx;
+        by = below ? nby : by;
+        Q *= g;
+    }
+    if (lane < 8) sig[lane] = pivot_rsqrt(mypq);
+    __syncwarp();
+    const double2 sxy = *reinterpret_cast<const double2*>(sig + j0);
+    const double si = sig[i];
+    lx = (j0 <= i) ? cx * sxy.x : 0.0;
+    ly = (j0 + 1 <= i) ? cy * sxy.y : 0.0;
+    wx = (j0 <= i) ? bx * si : 0.0;
+    wy = (j0 + 1 <= i) ? by * si : 0.0;
+}
+
 template <int VARIANT>
 __global__ void k(double* out, long long* cyc, int iters) {
     const int lane = threadIdx.x & 31, i = lane >> 2, j0 = 2 * (lane & 3);
@@ -146,6 +228,8 @@ int main() {
     run<1>("without the inverse (no second fragment)", out, cyc);
     run<2>("without the reciprocal square roots", out, cyc);
     run<3>("without the reciprocal approximation (alpha = 1)", out, cyc);
-    run<4>("kernel version: predicated FMAs, power-of-two scale", out, cyc);
+    run<4>("predicated FMAs, power-of-two scale", out, cyc);
+    run<5>("pivot row through shared memory instead of shuffles", out, cyc);
+    run<6>("... + power-of-two scale folded, one rsqrt per lane", out, cyc);
     return 0;
 }
