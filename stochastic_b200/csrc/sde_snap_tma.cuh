@@ -37,7 +37,7 @@ static_assert(SDE_SNAP_SWZ == 0 || SNAP_ROWB == (16 << SDE_SNAP_SWZ), "the swizz
 
 struct SnapWriter {
     unsigned char* base;   // this warp's boxes (generic pointer into shared memory, 1024-byte aligned)
-    u32 row;               // byte offset of this lane's row inside a box
+    u32 srow;              // shared-window address of this lane's row in box 0
     u32 xr;                // the row's swizzle term: chunk bits [4, 7) of an address are XORed with its bits [7, 10)
     u32 fill, snap0;       // snapshots in the tile, number of its first snapshot
     u64 warp_first;        // launch-relative index of the warp's first trajectory
@@ -45,11 +45,14 @@ struct SnapWriter {
 
     // `area`: first byte after the kernel's other dynamic shared memory; `warp_slot`: this warp's number among the
     // warps that store snapshots
-    __device__ __forceinline__ void init(unsigned char* area, const int warp_slot, const int lane_, const u64 warp_first_) {
+    __device__ __forceinline__ void init(unsigned char* area, const int warp_slot, const int, const u64 warp_first_) {
         const u32 a = (u32)__cvta_generic_to_shared(area);
         base = area + (((a + 1023u) & ~1023u) - a) + (size_t)warp_slot * SNAP_WARP_BYTES;
-        lane = lane_;
-        row = (u32)lane_ * SNAP_ROWB;
+        // the lane number through a volatile read: srow and xr then live in two registers for the whole run instead of
+        // being re-derived from the thread index at every snapshot (five instructions of the ~20 a snapshot cost)
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        const u32 row = (u32)lane * SNAP_ROWB;
+        srow = (u32)__cvta_generic_to_shared(base) + row;
         xr = ((row >> 7) & SNAP_SWZ_MASK) << 4;
         fill = 0;
         snap0 = 0;
@@ -61,12 +64,21 @@ struct SnapWriter {
         __syncwarp();
         snap0 = snap;
     }
+    __device__ __forceinline__ static void st_shared(const u32 addr, const double v) {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+    }
+    __device__ __forceinline__ static void st_shared(const u32 addr, const float v) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+    }
     // element `i` of a field of width W whose first box is `box0`, for snapshot `fill` of the tile
     template <int W>
     __device__ __forceinline__ void put(const int box0, const int i, const real v) {
-        const u32 e = fill * W + i;
-        const u32 off = (u32)(box0 + e / SNAP_TILE) * SNAP_BOXB + row + (((e % SNAP_TILE) * (u32)sizeof(real)) ^ xr);
-        *reinterpret_cast<real*>(base + off) = v;
+        if constexpr (W == 1) {   // one box: the swizzled column offset is the same for every scalar field of the snapshot
+            st_shared(srow + (u32)box0 * SNAP_BOXB + ((fill * (u32)sizeof(real)) ^ xr), v);
+        } else {
+            const u32 e = fill * W + i;
+            st_shared(srow + (u32)(box0 + e / SNAP_TILE) * SNAP_BOXB + (((e % SNAP_TILE) * (u32)sizeof(real)) ^ xr), v);
+        }
     }
     __device__ __forceinline__ static void store_box(const TensorMap* map, const unsigned char* box, const u32 c0, const u32 c1) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
