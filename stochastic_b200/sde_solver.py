@@ -311,13 +311,14 @@ def bead_regtile_block(n_beads):
     return 32 * (1 + max(1, nt // 2))
 
 
-def bead_regtile_smem_bytes(n_beads):
+def bead_regtile_smem_bytes(n_beads, twist=False):
     """Dynamic shared memory of the register-tiled bead kernel; mirrors RT_SMEM_DOUBLES of csrc/sde_bead_kernel.cuh."""
     npad = -(-3 * n_beads // 8) * 8
     nt = npad // 8
     npair = n_beads * (n_beads - 1) // 2
     dch = max(3, min(6, bead_regtile_block(n_beads) // n_beads))          # drift chunks per bead (RT_DCH)
-    return 8 * ((8 + dch) * npad + (4 + 6 * npair) + npair + (npair & 1) + 2 * nt * 64 + 128)
+    twsc = (n_beads // 2 - 1) * n_beads * 6 if twist else 0               # writhe gradients of the second segments (RT_TWSC)
+    return 8 * ((8 + dch) * npad + (4 + 6 * npair) + npair + (npair & 1) + 2 * nt * 64 + 128 + twsc)
 
 
 def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
@@ -644,7 +645,7 @@ class SDESolver:
         elem = 8 if f64 else 4
         workspace = None
         if plan.ks.traj_per_block == 2:            # register-tiled variant (traj_per_block doubles as its marker)
-            smem = bead_regtile_smem_bytes(nb)
+            smem = bead_regtile_smem_bytes(nb, bool(par.get("twist")))
             ctas_per_sm = max(1, min(2 if block > 170 else 3, (227 * 1024) // (smem + 1024)))
             npad = -(-d // 8) * 8
             # value-table indices of every (tile, lane), then 1024 CTA arrival counters per SM (must be zero)

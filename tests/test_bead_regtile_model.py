@@ -234,11 +234,14 @@ def test_shared_memory_size_and_block_formulas_match_the_header():
     assert bead_regtile_smem_bytes(5) == 8 * (14 * 16 + 64 + 10 + 256 + 128)
     assert bead_regtile_block(40) == 256 and bead_regtile_block(42) == 288 and bead_regtile_block(5) == 64
     assert 2 * (bead_regtile_smem_bytes(40) + 1024) <= 227 * 1024
+    # with the twist term: + [NB / 2 - 1][NB][6] writhe gradients of the second segments; still two CTAs per SM
+    assert bead_regtile_smem_bytes(40, twist=True) == bead_regtile_smem_bytes(40) + 8 * 19 * 40 * 6
+    assert 2 * (bead_regtile_smem_bytes(40, twist=True) + 2 * 1024 + 64) <= 228 * 1024
     import os
     import stochastic_b200
     header = open(os.path.join(os.path.dirname(stochastic_b200.__file__), "csrc", "sde_bead_kernel.cuh")).read()
     # the carve-up the formula mirrors
     for piece in ("RT_OFF_PART + RT_DCH * SDE_NP", "RT_OFF_YD + 4 * SDE_NP", "RT_OFF_VAL + RT_NVAL",
-                  "RT_OFF_OVL + RT_NPAIR + (RT_NPAIR & 1)", "RT_OFF_PAN + 2 * RT_NT * 64", "RT_OFF_LINV + 64", "RT_OFF_NEXTD + 64"):
+                  "RT_OFF_OVL + RT_NPAIR + (RT_NPAIR & 1)", "RT_OFF_PAN + 2 * RT_NT * 64", "RT_OFF_LINV + 64", "RT_OFF_NEXTD + 64", "RT_OFF_TWSC + RT_TWSC"):
         assert piece in header, piece
     assert re.search(r"SDE_BLOCK == 32 \* \(1 \+ RT_NBW\)", header)
