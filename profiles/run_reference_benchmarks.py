@@ -36,4 +36,4 @@ for name, scheme, n in cases:
                  "traj_steps_per_s": n * steps / med})
     print(json.dumps(rows[-1]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rows, open("gpurun_out/reference_benchmarks_r1.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/reference_benchmarks.json", "w"), indent=1)
