@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDEB200_ABI_VERSION 3
+#define SDEB200_ABI_VERSION 4   /* 4: TMA-storing programs (second kernel parameter built by sdeb200_solve), bead workspace carries zeroed CTA counters */
 
 typedef struct sdeb200_program sdeb200_program_t; /* a compiled (problem, scheme, dtype) kernel */
 

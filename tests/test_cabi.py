@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sdeb200.h but not exported"
     assert set(names) == set(runtime.EXPORTS)
-    assert lib.sdeb200_abi_version() == 3
+    assert lib.sdeb200_abi_version() == 4
 
 
 def test_nvrtc_is_bound_independently_of_the_host_process():
