@@ -96,5 +96,5 @@ def test_plain_c_client_builds_against_the_header_and_compiles_a_kernel(tmp_path
                            "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe, os.path.join(libdir, "csrc"), "4096"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    assert "sdeb200 ABI 3" in out.stdout and "compiled sde_solve_kernel for sm_100a" in out.stdout
+    assert "sdeb200 ABI 4" in out.stdout and "compiled sde_solve_kernel for sm_100a" in out.stdout
     assert ("no CUDA device" in out.stdout) or ("E[x_T]" in out.stdout)
