@@ -411,3 +411,44 @@ def test_host_side_stand_ins_for_post_processing_code():
     assert np.array_equal(jnp.ediff1d(msd, to_end=float("nan"))[:2], [1.0, 2.0])
     assert jnp.cov(rng.normal(size=(3, 40))).shape == (3, 3)
     assert jnp.pad(np.ones((2, 2)), ((0, 0), (0, 2))).shape == (2, 4)
+
+
+def test_tma_snapshot_tile_selection_and_emitted_defines():
+    """Which snapshot write-out a kernel gets (csrc/sde_snap_tma.cuh): TMA tiles whenever the output rows are 16-byte
+    multiples, with the longest row that keeps the kernel's occupancy; otherwise the transposed write-out loop."""
+    from stochastic_b200 import runtime
+    # fp64, d = m = 1: 128-byte rows fit the default budget, 64-byte rows the six-CTA budget of small step functions
+    assert runtime.pick_snap_tma(1, 1, 4, True, 0, 512) == (16, 3)
+    assert runtime.pick_snap_tma(1, 1, 4, True, 0, 512, budget=(227 * 1024) // 6 - 2048) == (8, 2)
+    assert runtime.pick_snap_tma(1, 1, 4, False, 0, 512) == (32, 3)                      # fp32: 32 snapshots per 128-byte row
+    assert runtime.pick_snap_tma(1, 1, 4, True, 0, 511) == (0, 0)                        # odd row length: no tensor map
+    assert runtime.pick_snap_tma(1, 1, 4, False, 0, 510) == (0, 0)
+    assert runtime.pick_snap_tma(1, 1, 4, True, 0, 6) == (4, 1)                          # short runs: rows no longer than the run
+    assert runtime.pick_snap_tma(1, 1, 4, True, 0, 2) == (0, 0)
+    assert runtime.pick_snap_tma(12, 12, 4, True, 0, 512) == (2, 0)                      # 25 boxes per warp: 16-byte rows
+    # the warp-specialised kernel: the ring leaves room for 16-byte rows of its four consumer warps only
+    ring = 2 * 46 * 128 * 8
+    assert runtime.pick_snap_tma(2, 2, 4, True, ring, 512, budget=(228 // 2 - 2) * 1024) == (2, 0)
+    assert runtime.snap_tma_bytes(2, 2, 4, True, 2) == 1024 + 4 * 5 * 32 * 16
+
+    prob, _ = P.gbm()
+    P.as_f64(prob)
+    src = build_source(prob.a, prob.b, 1, "euler", True, "original", n_snapshots=512)
+    assert "#define SDE_SNAP_TMA 8" in src.source and "#define SDE_SNAP_SWZ 2" in src.source
+    assert src.dyn_smem_bytes == 1024 + 4 * 3 * 32 * 64
+    odd = build_source(prob.a, prob.b, 1, "euler", True, "original", n_snapshots=511)
+    assert "SDE_SNAP_TMA" not in odd.source and "#define SDE_SNAP_TILE 16" in odd.source
+    final = build_source(prob.a, prob.b, 1, "euler", True, "original", n_snapshots=1)
+    assert "SDE_SNAP_TMA" not in final.source and "SDE_SNAP_TILE" not in final.source
+    old = pychastic.config.get("snapshot_tma")
+    try:
+        pychastic.config.update("snapshot_tma", False)
+        loop = build_source(prob.a, prob.b, 1, "euler", True, "original", n_snapshots=512)
+        assert "SDE_SNAP_TMA" not in loop.source and "#define SDE_SNAP_TILE 16" in loop.source
+    finally:
+        pychastic.config.update("snapshot_tma", old)
+    polar, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
+    P.as_f64(polar)
+    ws = build_source(polar.a, polar.b, 2, "wagner_platen", True, "original", n_snapshots=128)
+    assert "sde_kernel_ws.cuh" in ws.source and "#define SDE_SNAP_TMA 2" in ws.source and "#define SDE_SNAP_SWZ 0" in ws.source
+    assert ws.dyn_smem_bytes == ring + 1024 + 4 * 5 * 32 * 16
