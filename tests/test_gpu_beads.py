@@ -108,21 +108,26 @@ def test_twisted_ring_bead_kernel_equals_generic_traced_kernel(dtype, tol):
         assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
 
 
-@pytest.mark.parametrize("twist", [False, True])
-def test_register_tiled_and_shared_memory_variants_agree(twist):
-    """fp64, 40 beads: the register-tiled kernel (mobility and Cholesky factor in tensor-core accumulator fragments,
+@pytest.mark.parametrize("twist,n_beads", [(False, 40), (True, 40), (False, 42), (True, 41), (False, 11)])
+def test_register_tiled_and_shared_memory_variants_agree(twist, n_beads):
+    """fp64: the register-tiled kernel (mobility and Cholesky factor in tensor-core accumulator fragments,
     fraction-free factorisation of the diagonal tiles, row solves as tensor-core products, drift from the pair table,
-    noise folded into the row solves) against the shared-memory variant."""
-    prob = workloads.dna_loop(n_beads=40, tmax=1.2e-6, f64=True, twist=twist, x0=writhed_ring(40))
+    noise folded into the row solves) against the shared-memory variant.  40 beads = 15 tile rows (chain warp + 7 bulk
+    warps with two tile rows each); 41 / 42 beads = 16 tile rows (the last bulk warp owns one row; 42: odd / even ring for
+    the once-per-pair writhe sums); 11 beads = 5 tile rows with padding."""
+    prob = workloads.dna_loop(n_beads=n_beads, beam_length=n_beads / 40, tmax=1.2e-6, f64=True, twist=twist,
+                              x0=writhed_ring(n_beads, n_beads / 40))
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    solver.use_bead_kernel = True
     solver.bead_regtile = False
     b = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
     assert "SDE_BEAD_REGTILE 0" in solver._bead_plan(prob, True, "original").ks.source
     solver.bead_regtile = True
     a = solver.solve_many(prob, n_trajectories=5, seed=4, chunk_size=4)
     plan = solver._bead_plan(prob, True, "original")
-    assert "SDE_BEAD_REGTILE 1" in plan.ks.source and plan.ks.block == 256      # chain warp + 7 bulk warps
+    nt = -(-3 * n_beads // 8)
+    assert "SDE_BEAD_REGTILE 1" in plan.ks.source and plan.ks.block == 32 * (1 + nt // 2)      # chain warp + NT / 2 bulk warps
     for k in ("time_values", "solution_values", "wiener_values"):
         x, y = np.asarray(a[k]), np.asarray(b[k])
-        assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 120))
+        assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 3 * n_beads))
         assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
