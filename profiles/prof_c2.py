@@ -18,7 +18,7 @@ if os.environ.get("MINB"):
     solver.min_blocks_per_sm = int(os.environ["MINB"])
 if os.environ.get("WS"):
     solver.warp_specialize = bool(int(os.environ["WS"]))
-ws = {k: int(os.environ[k]) for k in ("SDE_WS_PGROUPS", "SDE_WS_CONSUMER_REGS", "SDE_WS_PRODUCER_REGS", "SDE_WS_GROUP", "SDE_WS_CTAIL", "SDE_LOGTAB_IN_SMEM")
+ws = {k: int(os.environ[k]) for k in ("SDE_WS_PGROUPS", "SDE_WS_CONSUMER_REGS", "SDE_WS_PRODUCER_REGS", "SDE_WS_GROUP", "SDE_WS_CTAIL", "SDE_LOGTAB_IN_SMEM", "SDE_WS_SPLIT_NORMAL")
       if os.environ.get(k)}
 if ws:
     solver.ws_tuning = ws

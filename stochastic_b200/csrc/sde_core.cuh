@@ -295,18 +295,20 @@ __device__ __forceinline__ float uniform_pm1(u32 bits) {
 // N standard normals at once: out[i] = element e[i] of jax.random.normal(key[i], shape with size[i]
 // elements, dtype).  Every stage is written group-wide so that the N dependent chains (20 threefry
 // rounds, the log, the 22-step Horner recurrence) are interleaved in the instruction stream.
-template <int N>
-__device__ __forceinline__ void normal_group(const Key (&key)[N], const u32 (&e)[N], const u32 (&size)[N],
-                                             real (&out)[N]) {
-    real x[N], w[N], p[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
+// The two halves of a draw, separately: the uniform variate in (-1, 1) (threefry2x32 + mantissa fill: integer work) and
+// sqrt(2) erf_inv of it (floating-point work).  normal_group below is their composition; the warp-specialised kernel can
+// also run them in different warps (SDE_WS_SPLIT_NORMAL: producers draw uniforms, consumers turn them into normals).
+__device__ __forceinline__ real uniform_elem(const Key key, const u32 e, const u32 size) {
 #if SDE_F64
-        x[i] = uniform_pm1(random_bits64(key[i], e[i], size[i]));
+    return uniform_pm1(random_bits64(key, e, size));
 #else
-        x[i] = uniform_pm1(random_bits32(key[i], e[i], size[i]));
+    return uniform_pm1(random_bits32(key, e, size));
 #endif
-    }
+}
+
+template <int N>
+__device__ __forceinline__ void normals_from_uniforms(const real (&x)[N], real (&out)[N]) {
+    real w[N], p[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) w[i] = erfinv_w(x[i]);
 #if SDE_F64
@@ -338,6 +340,15 @@ __device__ __forceinline__ void normal_group(const Key (&key)[N], const u32 (&e)
         out[i] = 1.41421354f * v;
     }
 #endif
+}
+
+template <int N>
+__device__ __forceinline__ void normal_group(const Key (&key)[N], const u32 (&e)[N], const u32 (&size)[N],
+                                             real (&out)[N]) {
+    real x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = uniform_elem(key[i], e[i], size[i]);
+    normals_from_uniforms<N>(x, out);
 }
 
 // one standard normal: element e of jax.random.normal(key, shape with `size` elements, dtype)

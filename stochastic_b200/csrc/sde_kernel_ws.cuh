@@ -46,6 +46,10 @@
 #ifndef SDE_WS_CTAIL
 #define SDE_WS_CTAIL 0                // of the 3M normals xi, mu, phi: how many (the last ones) the consumer draws itself
 #endif
+#ifndef SDE_WS_SPLIT_NORMAL
+#define SDE_WS_SPLIT_NORMAL 0         // 1: the producers draw UNIFORM variates (threefry: integer work only), the consumers
+                                      // turn them into normals (erf_inv: FP64 work, 46 independent chains per step)
+#endif
 #define SDE_WS_NC 128                 // consumer threads = trajectories per CTA
 #define SDE_WS_NP (128 * SDE_WS_PGROUPS)   // producer threads
 static_assert(SDE_BLOCK == SDE_WS_NC + SDE_WS_NP, "SDE_BLOCK must be 128 consumers + 128 per producer warpgroup");
@@ -111,6 +115,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
     sde_fill_logtab();
 #endif
 
+#if SDE_WS_SPLIT_NORMAL
+#define SDE_WS_DRAW uniform_elem
+    static_assert(SDE_WS_GROUP == 1 && SDE_WS_CTAIL == 0, "split normals: one draw at a time, none by the consumers");
+#else
+#define SDE_WS_DRAW normal_elem
+#endif
     if (!is_consumer) {
         // ================================ producers =====================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SDE_WS_PRODUCER_REGS));
@@ -143,7 +153,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                     const Key k = ser ? gen.k_eta : gen.k_zeta;
                     const int end = (ser + 1) * SDE_P * SDE_M;
 #pragma unroll 1
-                    for (; n < end; n += PG, e += PG, dst += PG * SLOT_BYTES) st_shared(dst, normal_elem(k, e, size));
+                    for (; n < end; n += PG, e += PG, dst += PG * SLOT_BYTES) st_shared(dst, SDE_WS_DRAW(k, e, size));
                     e -= (u32)(SDE_P * SDE_M);
                 }
                 // then the xi, mu, phi slots the consumer does not draw itself, same round-robin
@@ -151,7 +161,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
                 for (; n < SERIES + 3 * SDE_M - SDE_WS_CTAIL; n += PG, dst += PG * SLOT_BYTES) {
                     const int q = n - SERIES;
                     const Key k = (q < SDE_M) ? gen.k_xi : ((q < 2 * SDE_M) ? gen.k_mu : gen.k_phi);
-                    st_shared(dst, normal_elem(k, s * SDE_M + (u32)(q % SDE_M), S * SDE_M));
+                    st_shared(dst, SDE_WS_DRAW(k, s * SDE_M + (u32)(q % SDE_M), S * SDE_M));
                 }
             } else
 #pragma unroll 1
@@ -274,6 +284,30 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 2) sde_solve_kernel(cons
             const real* own = nullptr;
 #endif
             bar_sync(FULL0 + st, ALL);                         // normals of step g are in the ring
+#if SDE_WS_SPLIT_NORMAL
+            {   // uniforms -> normals in place, four independent chains at a time (this thread's column only)
+                real* const col = ring + (size_t)st * SDE_STAGE_COUNT * NC + c;
+                constexpr int NQ = SDE_STAGE_COUNT / 4 * 4;
+#pragma unroll 1
+                for (int n = 0; n < NQ; n += 4) {
+                    real u4[4], z4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) u4[q] = col[(n + q) * NC];
+                    normals_from_uniforms<4>(u4, z4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) col[(n + q) * NC] = z4[q];
+                }
+                if constexpr (SDE_STAGE_COUNT % 4 != 0) {
+                    constexpr int R = SDE_STAGE_COUNT % 4;
+                    real ur[R], zr[R];
+#pragma unroll
+                    for (int q = 0; q < R; ++q) ur[q] = col[(NQ + q) * NC];
+                    normals_from_uniforms<R>(ur, zr);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) col[(NQ + q) * NC] = zr[q];
+                }
+            }
+#endif
             Integrals I;
             // the stage is released as soon as its values sit in registers (only if a producer will wait for it)
             const bool release = g + 2 < total_steps;

@@ -215,7 +215,7 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         ]
         # measured on B200 (profiles/README.md): 3 producer warpgroups per consumer warpgroup, one normal at a time
         knobs = {"SDE_WS_PGROUPS": 3, "SDE_WS_CONSUMER_REGS": 136, "SDE_WS_PRODUCER_REGS": 40, "SDE_WS_GROUP": 1,
-                 "SDE_WS_CTAIL": 0, "SDE_LOGTAB_IN_SMEM": 1}
+                 "SDE_WS_CTAIL": 0, "SDE_LOGTAB_IN_SMEM": 1, "SDE_WS_SPLIT_NORMAL": 0}
         for knob, val in (ws_tuning or {}).items():
             if knob not in knobs:
                 raise KeyError(f"unknown warp-specialisation knob {knob!r}")
@@ -229,6 +229,8 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         parts.append(f"#define SDE_BLOCK {ws_block}")
         for knob, val in knobs.items():
             parts.append(f"#define {knob} {val}")
+        if knobs["SDE_WS_SPLIT_NORMAL"]:
+            parts.append("#define SDE_TAIL_ATTR __forceinline__")        # (same ptxas issue as below)
         if knobs["SDE_WS_CTAIL"]:
             if not 0 < knobs["SDE_WS_CTAIL"] <= 3 * m or knobs["SDE_WS_GROUP"] != 1:
                 raise ValueError("SDE_WS_CTAIL must be in [0, 3m] and needs SDE_WS_GROUP == 1")

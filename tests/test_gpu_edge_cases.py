@@ -188,15 +188,19 @@ def test_very_short_runs_in_both_stepping_kernels(n_steps, warp_specialize):
 
 
 def test_both_stepping_kernels_agree_bit_for_bit():
+    """Single-role kernel, warp-specialised kernel, and the warp-specialised kernel whose producers draw uniforms and
+    whose consumers apply erf_inv (SDE_WS_SPLIT_NORMAL, a measured-and-rejected variant kept as a tuning knob)."""
     prob, _ = P.polar_walk(4.0, (2.0, 0.0), 1.0)
     P.as_f64(prob)
     out = []
-    for ws in (True, False):
+    for ws, tuning in ((True, None), (False, None), (True, {"SDE_WS_SPLIT_NORMAL": 1})):
         solver = pychastic.sde_solver.SDESolver(scheme="wagner_platen", dt=2 ** -5)
         solver.warp_specialize = ws
+        solver.ws_tuning = tuning
         out.append(solver.solve_many(prob, n_trajectories=777, seed=5, chunk_size=4, chunks_per_randomization=2))
-    for k in ("time_values", "solution_values", "wiener_values"):
-        assert np.array_equal(np.asarray(out[0][k]), np.asarray(out[1][k]))
+    for other in out[1:]:
+        for k in ("time_values", "solution_values", "wiener_values"):
+            assert np.array_equal(np.asarray(out[0][k]), np.asarray(other[k]))
 
 
 def _stores_three_ways(prob, scheme, dt, n_traj, tma_choices, **kw):
