@@ -131,3 +131,22 @@ def test_register_tiled_and_shared_memory_variants_agree(twist, n_beads):
         x, y = np.asarray(a[k]), np.asarray(b[k])
         assert x.shape == y.shape == ((5, 3) if k == "time_values" else (5, 3, 3 * n_beads))
         assert np.abs(x - y).max() <= 1e-11 * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
+
+
+@pytest.mark.parametrize("twist", [False, True])
+def test_ctas_that_integrate_several_trajectories_in_a_row(twist):
+    """The bead kernel launches at most two CTAs per SM and every CTA loops over trajectories: a run with more
+    trajectories than CTAs must equal the same trajectories integrated in shards that fit in one wave (every CTA exactly
+    one trajectory) - nothing may leak from one trajectory of a CTA into its next."""
+    prob = workloads.dna_loop(n_beads=40, tmax=3.5e-7, f64=True, twist=twist, x0=writhed_ring(40))
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    n = 700                                             # 148 SMs x 2 CTAs = 296 CTAs: three trajectories for some CTAs
+    full = solver.solve_many(prob, n_trajectories=n, seed=9, chunk_size=None)
+    x_full = np.asarray(full["solution_values"])
+    assert x_full.shape == (n, 1, 120) and np.isfinite(x_full).all()
+    for begin in range(0, n, 175):
+        part = solver.solve_many(prob, n_trajectories=n, seed=9, chunk_size=None, traj_range=(begin, 175))
+        for k in ("time_values", "solution_values", "wiener_values"):
+            assert np.array_equal(np.asarray(full[k])[begin:begin + 175], np.asarray(part[k])), (k, begin)
+    # and the trajectories differ from each other (distinct keys)
+    assert np.unique(x_full[:, 0, 0]).size == n
