@@ -79,6 +79,25 @@ def test_dna_loop_with_twist_matches_oracle():
     assert np.abs(np.asarray(plain["solution_values"]) - ref["solution_values"]).max() > 1e-7
 
 
+@pytest.mark.parametrize("twist", [False, True])
+def test_dna_loop_mid_size_matches_oracle(twist):
+    """12 trajectories x 60 steps from a writhed ring with jittered beads (stretched / compressed springs, overlapping and
+    non-overlapping RPY pairs, beads inside the steric contact range): every stored snapshot against the oracle."""
+    rng = np.random.default_rng(5)
+    x0 = writhed_ring(40) + 0.1 / 40 * rng.standard_normal((40, 3))
+    prob = workloads.dna_loop(n_beads=40, tmax=60e-7, f64=True, twist=twist, x0=x0)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    got = solver.solve_many(prob, n_trajectories=12, seed=11, chunk_size=15)
+    ref = osolver.solve_many(oprob.dna_loop(40, tmax=60e-7, twist=twist, x0=x0), scheme="euler", dt=1e-7,
+                             n_trajectories=12, seed=11, chunk_size=15, dtype=np.float64)
+    assert ref["solution_values"].shape == (12, 4, 120)
+    assert np.abs(ref["solution_values"][:, -1] - x0.reshape(-1)).max() > 0.5 / 40      # the beads really moved
+    for k in ("time_values", "solution_values", "wiener_values"):
+        g, r = np.asarray(got[k]), ref[k]
+        assert g.shape == r.shape, (k, g.shape, r.shape)
+        assert np.abs(g - r).max() <= 1e-9 * max(np.abs(r).max(), 1e-12), (k, np.abs(g - r).max())
+
+
 def test_small_rings_on_the_register_tiled_kernel():
     """5 and 6 beads (2 and 3 tile rows, mostly padding) on the register-tiled kernel against the generic traced one."""
     for nb in (5, 6):
