@@ -336,6 +336,8 @@ def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
         f"#define SDE_BEAD_TIMING {int(os.environ.get('SDEB200_BEAD_TIMING', '0'))}",   # diagnostics: per-phase cycle counts
         *([f"#define SDE_BEAD_EXPERIMENT_SKIP {int(os.environ['SDEB200_BEAD_SKIP'])}"] if os.environ.get("SDEB200_BEAD_SKIP") else []),
         *([f"#define SDE_BEAD_UPD_GROUP {int(os.environ['SDEB200_BEAD_UPD_GROUP'])}"] if os.environ.get("SDEB200_BEAD_UPD_GROUP") else []),
+        *([f"#define SDE_BEAD_FACTOR_DMMA {int(os.environ['SDEB200_BEAD_FACTOR_DMMA'])}"] if os.environ.get("SDEB200_BEAD_FACTOR_DMMA") else []),
+        *([f"#define SDE_BEAD_FENCES {int(os.environ['SDEB200_BEAD_FENCES'])}"] if os.environ.get("SDEB200_BEAD_FENCES") else []),
         '#include "sde_bead_kernel.cuh"', ""])
 
 

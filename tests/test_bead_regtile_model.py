@@ -1,7 +1,7 @@
 """Host model of the register-tiled bead kernel (csrc/sde_bead_kernel.cuh, SDE_BEAD_REGTILE): the same tile ownership,
 fragment layouts, buffer indexing and phase order, executed lane by lane in numpy.  Checks that the data flow of the
-kernel - mobility tiles built from the pair table in accumulator-fragment order, the fraction-free factorisation of the
-diagonal tile with its inverse, the row solves as tensor-core products with a permuted contraction index, the
+kernel - mobility tiles built from the pair table in accumulator-fragment order, the factorisation of the diagonal tile
+with its inverse as rank-one tensor-core updates, the row solves as tensor-core products with a permuted contraction index, the
 double-buffered panel, the catch-up of the diagonal tiles, noise folded into the row solves, drift from the pair
 table - computes chol(mu) xi and mu F.  (The arithmetic itself is checked on the GPU against the oracle.)"""
 import re
@@ -29,28 +29,64 @@ def dmma884(c, a, b):
     return out
 
 
-def factor_fraction_free(frag, rng):
-    """`factor_fraction_free` of the header: fraction-free elimination of [C | 1], every lane two entries of each."""
-    c = frag.copy()
+def shfl(v, src):
+    """shfl.sync.idx of a 32-lane register: lane l reads lane src[l] (or the one lane src)."""
+    return v[np.broadcast_to(src, (32,))]
+
+
+def factor_rank_one(frag, rng):
+    """`factor_rank_one` of the header, lane by lane: one tile (S in the lower triangle, T = B^T in the strict upper one),
+    one DMMA per pivot on the masked column register, the next pivot predicted from two broadcasts, reciprocals with the
+    accuracy of rcp.approx + the two-term correction.  Returns the fragments of L and of inv(L) TRANSPOSED."""
     i, j0 = ROW, 2 * QD
-    b = np.stack([(j0 == i) * 1.0, (j0 + 1 == i) * 1.0], axis=1)
-    Q, sx, sy, si = 1.0, np.zeros(32), np.zeros(32), np.zeros(32)
-    for k in range(8):
-        ck = c[:, k & 1]
-        ckk = ck[4 * k + (k >> 1)]
-        cik, cj0, cj1 = ck[4 * i + (k >> 1)], ck[4 * j0 + (k >> 1)], ck[4 * (j0 + 1) + (k >> 1)]
-        bk0, bk1 = b[4 * k + QD, 0], b[4 * k + QD, 1]
-        alpha = (1.0 / ckk) * (1.0 + 2.0 ** -20 * rng.uniform(-1, 1))       # rcp.approx: ~20 good bits
-        sigma = 1.0 / np.sqrt(Q * ckk)
-        sx, sy, si = np.where(j0 == k, sigma, sx), np.where(j0 + 1 == k, sigma, sy), np.where(i == k, sigma, si)
-        c[:, 0] = np.where((i > k) & (j0 > k), (ckk * c[:, 0] - cik * cj0) * alpha, c[:, 0])
-        c[:, 1] = np.where((i > k) & (j0 + 1 > k), (ckk * c[:, 1] - cik * cj1) * alpha, c[:, 1])
-        b[:, 0] = np.where(i > k, (ckk * b[:, 0] - cik * bk0) * alpha, b[:, 0])
-        b[:, 1] = np.where(i > k, (ckk * b[:, 1] - cik * bk1) * alpha, b[:, 1])
-        Q *= ckk * alpha
-    L = np.stack([np.where(j0 <= i, c[:, 0] * sx, 0.0), np.where(j0 + 1 <= i, c[:, 1] * sy, 0.0)], axis=1)
-    W = np.stack([np.where(j0 <= i, b[:, 0] * si, 0.0), np.where(j0 + 1 <= i, b[:, 1] * si, 0.0)], axis=1)
-    return L, W
+    cx = np.where(j0 > i, 0.0, frag[:, 0])
+    cy = np.where(j0 + 1 > i, 0.0, frag[:, 1])
+
+    def recip(d):
+        a = (1.0 / d) * (1.0 + 2.0 ** -22 * rng.uniform(-1, 1))          # rcp.approx: ~22 good bits
+        r = 1.0 - d * a
+        a = a + a * r
+        return a + a * (r * r)
+
+    d = shfl(cx, 0)
+    px, py = d.copy(), np.ones(32)
+    a = recip(d)
+    for k in range(7):
+        ck = cy if k & 1 else cx
+        mine = QD == (k >> 1)
+        ub = np.where(mine & (i > k), ck, 0.0)
+        ua = np.where(mine, np.where(i == k, 1.0, ck), 0.0)
+        P = dmma884(np.zeros((32, 2)), ua, ub)
+        e = shfl(cy if (k + 1) & 1 else cx, 4 * (k + 1) + ((k + 1) >> 1))
+        w = shfl(ck, 4 * (k + 1) + (k >> 1))
+        dn = e - a * w * w
+        if (k + 1) & 1:
+            py = np.where(j0 == k, dn, py)
+        else:
+            px = np.where(j0 == k + 1, dn, px)
+        cx = np.where((i > k) & (j0 > i), cx, cx - a * P[:, 0])
+        cy = np.where((i > k) & (j0 + 1 > i), cy, cy - a * P[:, 1])
+        a = recip(dn)
+    sx, sy = 1.0 / np.sqrt(px), 1.0 / np.sqrt(py)
+    L = np.stack([np.where(j0 <= i, cx * sx, 0.0), np.where(j0 + 1 <= i, cy * sy, 0.0)], axis=1)
+    WT = np.stack([np.where(j0 > i, cx * sx, np.where(j0 == i, sx, 0.0)),
+                   np.where(j0 + 1 > i, cy * sy, np.where(j0 + 1 == i, sy, 0.0))], axis=1)
+    return L, WT
+
+
+def test_rank_one_factorisation_of_a_tile():
+    """L L^T = C and inv(L) L = 1 for random SPD tiles, from the lane-level model of the tensor-core factorisation."""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        G = rng.standard_normal((8, 12))
+        C = G @ G.T / 12 + 0.5 * np.eye(8)
+        frag = np.stack([C[ROW, 2 * QD], C[ROW, 2 * QD + 1]], axis=1)
+        Lf, WTf = factor_rank_one(frag, rng)
+        L, WT = np.zeros((8, 8)), np.zeros((8, 8))
+        L[ROW, 2 * QD], L[ROW, 2 * QD + 1] = Lf[:, 0], Lf[:, 1]
+        WT[ROW, 2 * QD], WT[ROW, 2 * QD + 1] = WTf[:, 0], WTf[:, 1]
+        assert np.allclose(L, np.linalg.cholesky(C), rtol=1e-12, atol=1e-14)
+        assert np.allclose(WT.T @ L, np.eye(8), rtol=0, atol=1e-12)
 
 
 def slots_of(b, NT):
@@ -162,8 +198,8 @@ def test_register_tiled_cholesky_data_flow(nb):
     cur = fragment(0, 0)
     for p in range(NT):
         # chain warp: factor, publish the inverse, the diagonal rows' terms of y (four partial sums per row)
-        L, W = factor_fraction_free(cur, rng)
-        Linv[OFF], Linv[OFF + 1] = W[:, 0], W[:, 1]
+        L, WT = factor_rank_one(cur, rng)
+        Linv[8 * (2 * QD) + ROW], Linv[8 * (2 * QD + 1) + ROW] = WT[:, 0], WT[:, 1]      # published row-major: inv(L)[j][i]
         yd4[4 * 8 * p + LANES] = L[:, 0] * xi[8 * p + 2 * QD] + L[:, 1] * xi[8 * p + 2 * QD + 1]
         if p + 1 == NT:
             break
