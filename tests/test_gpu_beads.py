@@ -169,3 +169,56 @@ def test_ctas_that_integrate_several_trajectories_in_a_row(twist):
             assert np.array_equal(np.asarray(full[k])[begin:begin + 175], np.asarray(part[k])), (k, begin)
     # and the trajectories differ from each other (distinct keys)
     assert np.unique(x_full[:, 0, 0]).size == n
+
+
+@pytest.mark.parametrize("twist", [False, True])
+def test_one_step_of_1e5_rings_has_the_mobility_as_covariance(twist):
+    """BASELINE config C4's trajectory count, size-independent property: one Euler step from x0 is
+    x0 + a(x0) dt + sqrt(2 dt) chol(mu(x0)) xi, so over 10^5 trajectories the displacement has mean a(x0) dt and covariance
+    2 dt mu(x0) (mu and a from the oracle).  Sampling errors: Wishart, E|C_hat - C|_F^2 = (|C|_F^2 + tr(C)^2) / n."""
+    import torch
+    n, dt = 100_000, 1e-7
+    x0 = writhed_ring(40)
+    prob = workloads.dna_loop(n_beads=40, tmax=1.5e-7, f64=True, twist=twist, x0=x0)
+    sol = pychastic.sde_solver.SDESolver(scheme="euler", dt=dt).solve_many(prob, n_trajectories=n, seed=7, chunk_size=None)
+    x1 = np.asarray(sol["solution_values"])[:, -1, :]
+    assert x1.shape == (n, 120) and np.isfinite(x1).all()
+    oracle = oprob.dna_loop(40, tmax=1.5e-7, twist=twist, x0=x0)
+    xt = torch.as_tensor(x0.reshape(-1))
+    drift, noise = oracle.a(xt).numpy(), oracle.b(xt).numpy()
+    cov = dt * noise @ noise.T                                       # = 2 dt mu
+    disp = x1 - x0.reshape(-1)
+    mean_err = np.abs(disp.mean(0) - drift * dt) / np.sqrt(np.diag(cov) / n)
+    assert mean_err.max() < 5.0, mean_err.max()                      # 120 components, 5 standard errors
+    c_hat = np.cov(disp, rowvar=False)
+    expected = np.sqrt((np.sum(cov ** 2) + np.trace(cov) ** 2) / n)
+    err = np.linalg.norm(c_hat - cov)
+    assert err < 1.5 * expected, (err, expected)
+    assert err > 0.5 * expected, (err, expected)                     # (and not suspiciously exact: the draws are independent)
+    # the Wiener increments returned beside the state are the xi of that step: x1 - x0 - a dt = b(x0) w
+    w = np.asarray(sol["wiener_values"])[:, -1, :]
+    assert np.abs(disp - drift * dt - w @ noise.T).max() < 1e-12
+
+
+def test_baseline_config_c4_full_size_keeps_the_rings_intact():
+    """BASELINE config C4 as stated (10^5 trajectories x 1000 steps, dt = 1e-7, final state only): every ring is finite,
+    connected (bonds within 30 % of the rest length, thermal width as the stretch modulus says), distinct, and the ensemble has not drifted
+    (centre of mass: pure diffusion, mean within 5 standard errors of zero)."""
+    n, steps = 100_000, 1000
+    prob = workloads.dna_loop(n_beads=40, tmax=(steps + 0.5) * 1e-7, f64=True)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    sol = solver.solve_many(prob, n_trajectories=n, seed=3, chunk_size=None)
+    assert solver.last_steps == steps
+    x = np.asarray(sol["solution_values"])[:, -1, :].reshape(n, 40, 3)
+    assert np.isfinite(x).all()
+    bonds = np.linalg.norm(x - np.roll(x, 1, axis=1), axis=2)
+    assert 0.7 / 40 < bonds.min() and bonds.max() < 1.3 / 40, (bonds.min(), bonds.max())
+    # the bonds have equilibrated (relaxation time 1 / (2 mu ks) ~ a step): Boltzmann width sqrt(kT / ks), widened by the
+    # Euler step (stationary variance (kT / ks) / (1 - lambda dt / 2) with lambda dt ~ 0.5 - 1)
+    width = np.sqrt(1.0 / prob.bead_ring["ks"])
+    assert 0.9 * width < bonds.std() < 1.5 * width, (bonds.std(), width)
+    cm = x.mean(1) - np.asarray(prob.x0).reshape(40, 3).mean(0)
+    assert np.abs(cm.mean(0)).max() < 5 * cm.std(0).max() / np.sqrt(n)
+    assert cm.std(0).min() > 0 and len(np.unique(x[:, 0, 0])) == n
+    t = np.asarray(sol["time_values"])
+    assert np.allclose(t[:, -1], steps * 1e-7, rtol=1e-12)
