@@ -10,6 +10,9 @@
   the STORED Wiener path bounds the pathwise error of every snapshot (reference tests/test_sde_solver.py:14-47), and
   time_values is the same arithmetic progression for every trajectory.
 * C5 (GARCH, moments only): sharded moments add up to the unsharded moments.
+* C3 (two RPY spheres on a spring, 10^6 trajectories): the separation reaches its Boltzmann law r^2 exp(-U(r)) - the
+  fluctuation-dissipation balance of drift = mu F and noise = sqrt(2) chol(mu); shards equal the full run.
+(C4 at its full size: tests/test_gpu_beads.py.)
 """
 import numpy as np
 import pytest
@@ -106,3 +109,31 @@ def test_c5_sharded_moments_add_up():
     assert np.allclose(tot, np.asarray(full["moments"]), rtol=1e-11)
     price = np.asarray(full["moments"])[0, 0] / n
     assert 5.9 < price < 6.2                                  # 6.0282 +- 0.0005 at 10^9 paths (profiles/README.md)
+
+
+def test_c3_full_size_spring_length_is_boltzmann_distributed():
+    """BASELINE config C3 (two RPY spheres of radii 1 and 0.2 on the spring U = (r - 4)^2, Euler dt = 0.01, 10^6 trajectories;
+    reference examples/example_two_interacting_brownian_spheres.py:17-37), run for 1000 steps - twice the 500 of the config, six
+    relaxation times of the spring - so that the separation has reached its equilibrium law p(r) ~ r^2 exp(-U(r)) whatever
+    the (configuration dependent) mobility is: that is the fluctuation-dissipation balance between drift = mu F and
+    noise = sqrt(2) chol(mu) the whole kernel exists to keep.  Also: shards of the global fan-out equal the full run."""
+    n = 10 ** 6
+    prob = workloads.two_spheres(tmax=10.0, f64=True)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=0.01)
+    sol = solver.solve_many(prob, n_trajectories=n, seed=0, chunk_size=None)
+    assert solver.last_steps == 1000
+    x = _t(sol["solution_values"])[:, -1, :]
+    assert x.shape == (n, 6) and bool(torch.isfinite(x).all())
+    r = torch.linalg.norm(x[:, 3:] - x[:, :3], dim=1)
+    grid = np.linspace(0.0, 12.0, 120001)
+    p = grid ** 2 * np.exp(-(grid - 4.0) ** 2)
+    p /= np.trapezoid(p, grid)
+    mean = np.trapezoid(grid * p, grid)
+    var = np.trapezoid((grid - mean) ** 2 * p, grid)
+    assert abs(float(r.mean()) - mean) < 0.01 * mean, (float(r.mean()), mean)          # 4.24; sampling error 0.0007
+    assert abs(float(r.var()) / var - 1.0) < 0.03, (float(r.var()), var)                # Euler bias ~ mu_rel U'' dt / 2 = 0.3 %
+    # the spheres diffuse with very different mobilities: the small one has moved much further
+    msd_big, msd_small = float((x[:, :3] ** 2).sum(1).mean()), float(((x[:, 3:] - torch.tensor([0.0, 0.0, 4.0], device=x.device)) ** 2).sum(1).mean())
+    assert msd_small > 2.0 * msd_big > 0
+    part = solver.solve_many(prob, n_trajectories=n, seed=0, chunk_size=None, traj_range=(333_333, 1001))
+    assert torch.equal(_t(part["solution_values"])[:, -1, :], x[333_333:334_334])
