@@ -98,6 +98,23 @@ def test_dna_loop_mid_size_matches_oracle(twist):
         assert np.abs(g - r).max() <= 1e-9 * max(np.abs(r).max(), 1e-12), (k, np.abs(g - r).max())
 
 
+@pytest.mark.parametrize("regtile", [None, False])
+def test_strongly_overlapping_beads_match_oracle(regtile):
+    """A ring 2.5 times shorter than the reference's: neighbours sit at 0.78 hydrodynamic radii and every bead overlaps its four
+    nearest neighbours (the overlapping-spheres branch of RPY everywhere near the diagonal, steric contact for two neighbours
+    on each side), mobility condition number 140 - the factorisation's pivots shrink to a twelfth of the diagonal."""
+    kw = dict(n_beads=40, beam_length=0.4, tmax=8e-8)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=2e-8)
+    solver.bead_regtile = regtile
+    got = solver.solve_many(workloads.dna_loop(f64=True, **kw), n_trajectories=3, seed=2, chunk_size=2)
+    ref = osolver.solve_many(oprob.dna_loop(40, beam_length=0.4, tmax=8e-8), scheme="euler", dt=2e-8, n_trajectories=3,
+                             seed=2, chunk_size=2, dtype=np.float64)
+    for k in ("time_values", "solution_values", "wiener_values"):
+        g, r = np.asarray(got[k]), ref[k]
+        assert g.shape == r.shape, (k, g.shape, r.shape)
+        assert np.abs(g - r).max() <= 1e-9 * max(np.abs(r).max(), 1e-12), (k, np.abs(g - r).max())
+
+
 def test_small_rings_on_the_register_tiled_kernel():
     """5 and 6 beads (2 and 3 tile rows, mostly padding) on the register-tiled kernel against the generic traced one."""
     for nb in (5, 6):
