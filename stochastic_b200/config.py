@@ -15,6 +15,11 @@ _STATE = {
     # divisions become multiplications (an FP64 division costs ~12 instructions on the GPU).  Changes the last bit of
     # those quotients, so it is opt-in: the default keeps the operations the user's functions spell out.
     "reciprocal_division": False,
+    # `jnp.linalg.cholesky` on traced fp64 input: pivot j contributes ONE reciprocal square root (L_jj = s rsqrt(s), the
+    # column is multiplied by rsqrt(s)) instead of a square root and a division - 1-ulp `rsqrt` of the CUDA math library, a
+    # fifth of the instructions (two spheres / four beads + 4-5 %, results move by 6e-16).  fp32 keeps sqrt + division.  (How a library routine forms its factor is the library's choice - XLA's
+    # expander makes its own - so this is not covered by "reciprocal_division"; False restores sqrt + division.)
+    "cholesky_rsqrt": True,
     # Stored trajectories: hand whole snapshot tiles (32 trajectories x 16..128 bytes per field column) to the TMA
     # unit (csrc/sde_snap_tma.cuh) whenever the output rows are 16-byte multiples.  False: the warp-transposed
     # write-out loop of csrc/sde_kernel.cuh (also the fallback for rows a tensor map cannot describe).

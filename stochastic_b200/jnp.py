@@ -16,6 +16,7 @@ import builtins
 
 import numpy as _np
 
+from . import config
 from .trace import expr as E
 
 pi = _np.pi
@@ -320,9 +321,13 @@ class _Linalg:
             s = E.wrap(a[j, j])
             for k in range(j):
                 s = s - L[j, k] * L[j, k]
-            d = E.unary("sqrt", s)
-            L[j, j] = d
-            inv = E.div(E.ONE, d)
+            if config.get("cholesky_rsqrt") and E.TRACE_F64:
+                inv = E.unary("rsqrt", s)
+                L[j, j] = s * inv
+            else:
+                d = E.unary("sqrt", s)
+                L[j, j] = d
+                inv = E.div(E.ONE, d)
             for i in range(j + 1, n):
                 s = E.wrap(a[i, j])
                 for k in range(j):

@@ -194,6 +194,7 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
 
     Returns a `KernelSource`."""
     E.trim_table()
+    E.TRACE_F64 = bool(f64)
     tp = TracedProblem(problem_a, problem_b, d)
     m = tp.m
     outs, sv = step_expressions(tp, scheme)
@@ -416,7 +417,8 @@ class SDESolver:
     def _knobs(self):
         return (self.block_size, self.min_blocks_per_sm, self.lockstep, self.snap_tile, self.warp_specialize,
                 tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel, self.bead_regtile,
-                config.get("warp_specialize"), config.get("reciprocal_division"), config.get("snapshot_tma"))
+                config.get("warp_specialize"), config.get("reciprocal_division"), config.get("snapshot_tma"),
+                config.get("cholesky_rsqrt"))
 
     @staticmethod
     def _uses_bead_kernel(problem, force):

@@ -111,7 +111,8 @@ def emit_body(outputs, var_names, f64=True, lang="cuda", indent="    ", reciproc
         elif op == "sign":
             rhs = f"(real)(({a[0]} > 0) - ({a[0]} < 0))"
         elif op == "rsqrt":
-            rhs = f"(real)1 / sqrt{suffix}({a[0]})"
+            # CUDA: the math library's rsqrt (1 ulp in fp64, no division); fp32 and host C: 1 / sqrt, both correctly rounded
+            rhs = f"rsqrt({a[0]})" if (lang == "cuda" and f64) else f"(real)1 / sqrt{suffix}({a[0]})"
         elif op == "where":
             rhs = f"{a[0]} ? {a[1]} : {a[2]}"
         elif op in _CMP:

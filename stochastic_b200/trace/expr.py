@@ -18,6 +18,8 @@ import numpy as np
 _TABLE = {}
 _COUNTER = [0]
 
+TRACE_F64 = True     # working precision of the trace in progress (set by sde_solver.build_source; library routines may pick
+                     # their formulation by it, e.g. jnp.linalg.cholesky)
 UNARY_FUNCS = ("neg", "sin", "cos", "tan", "exp", "log", "sqrt", "tanh", "sinh", "cosh", "atan",
                "asin", "acos", "abs", "sign", "log1p", "expm1", "floor", "trunc", "not", "erf", "rsqrt")
 BINARY_FUNCS = ("add", "sub", "mul", "div", "pow", "max", "min", "fmod", "atan2",
@@ -449,7 +451,7 @@ def _diff(e, v, memo):
         elif op == "sqrt":
             r = div(d[0], mul(TWO, e))
         elif op == "rsqrt":
-            r = mul(mul(const(-0.5), div(e, a[0])), d[0])
+            r = mul(mul(const(-0.5), mul(e, mul(e, e))), d[0])       # -1/2 s^(-3/2): no division
         elif op == "tanh":
             r = mul(sub(ONE, mul(e, e)), d[0])
         elif op == "sinh":

@@ -452,3 +452,48 @@ def test_tma_snapshot_tile_selection_and_emitted_defines():
     ws = build_source(polar.a, polar.b, 2, "wagner_platen", True, "original", n_snapshots=128)
     assert "sde_kernel_ws.cuh" in ws.source and "#define SDE_SNAP_TMA 2" in ws.source and "#define SDE_SNAP_SWZ 0" in ws.source
     assert ws.dyn_smem_bytes == ring + 1024 + 4 * 5 * 32 * 16
+
+
+def test_traced_cholesky_uses_one_reciprocal_square_root_per_pivot_in_fp64():
+    """`jnp.linalg.cholesky` on traced input (config "cholesky_rsqrt"): fp64 kernels form the factor from rsqrt alone, fp32
+    kernels and the switched-off configuration from sqrt + one division per pivot; the three agree as functions."""
+    import re
+    from stochastic_b200 import workloads
+    from stochastic_b200.trace import emit
+    prob64, prob32 = workloads.two_spheres(tmax=1.0, f64=True), workloads.two_spheres(tmax=1.0, f64=False)
+
+    def step_text(prob, f64):
+        src = build_source(prob.a, prob.b, 6, "euler", f64, "original").source
+        return src[src.index("sde_step"):]
+
+    def count(text, fn):
+        return len(re.findall(r"\b" + fn + r"\(", text))
+
+    s64 = step_text(prob64, True)
+    n_piv = count(s64, "rsqrt")                 # (equal pivots - the three of a sphere's own block - are one expression)
+    assert 3 <= n_piv <= 6
+    s32 = step_text(prob32, False)
+    assert count(s32, "rsqrt") == 0 and count(s32, "sqrt") == count(s64, "sqrt") + n_piv
+    old = pychastic.config.get("cholesky_rsqrt")
+    try:
+        pychastic.config.update("cholesky_rsqrt", False)
+        off = step_text(prob64, True)
+    finally:
+        pychastic.config.update("cholesky_rsqrt", old)
+    assert count(off, "rsqrt") == 0 and count(off, "sqrt") == count(s64, "sqrt") + n_piv
+    assert off.count(" / ") > s64.count(" / ")                   # and the pivots' divisions
+    # same function: the symbolic factor evaluated on the host at a random configuration
+    from stochastic_b200 import numpy as jnp_
+    from stochastic_b200.trace import expr as E
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((5, 7))
+    C = G @ G.T + np.eye(5)
+    for flag in (True, False):
+        pychastic.config.update("cholesky_rsqrt", flag)
+        try:
+            xs = [E.var(k) for k in range(25)]
+            L = jnp_.linalg.cholesky(np.array(xs, dtype=object).reshape(5, 5).view(type(jnp_.asarray(xs))))
+            vals = E.evaluate([E.wrap(v) for v in np.asarray(L, dtype=object).ravel()], C.ravel())
+        finally:
+            pychastic.config.update("cholesky_rsqrt", old)
+        assert np.allclose(np.array(vals).reshape(5, 5), np.linalg.cholesky(C), rtol=1e-13, atol=1e-15)
