@@ -1,5 +1,5 @@
 """Traced bead problems (symbolic Cholesky of the mobility) with the factor formed from one reciprocal square root per pivot
-(config "cholesky_rsqrt", default) or from a square root and a division: python profiles/run_cholesky_rsqrt.py"""
+(config "library_rsqrt", default) or from a square root and a division: python profiles/run_library_rsqrt.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,7 +14,7 @@ CASES = [("C3 two RPY spheres, fp64 Euler", lambda: workloads.two_spheres(tmax=5
 for name, make, scheme, dt, n in CASES:
     out = {}
     for flag in (False, True):
-        pychastic.config.update("cholesky_rsqrt", flag)
+        pychastic.config.update("library_rsqrt", flag)
         prob = make()
         solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
         best = float("inf")

@@ -15,11 +15,13 @@ _STATE = {
     # divisions become multiplications (an FP64 division costs ~12 instructions on the GPU).  Changes the last bit of
     # those quotients, so it is opt-in: the default keeps the operations the user's functions spell out.
     "reciprocal_division": False,
-    # `jnp.linalg.cholesky` on traced fp64 input: pivot j contributes ONE reciprocal square root (L_jj = s rsqrt(s), the
-    # column is multiplied by rsqrt(s)) instead of a square root and a division - 1-ulp `rsqrt` of the CUDA math library, a
-    # fifth of the instructions (two spheres / four beads + 4-5 %, results move by 6e-16).  fp32 keeps sqrt + division.  (How a library routine forms its factor is the library's choice - XLA's
-    # expander makes its own - so this is not covered by "reciprocal_division"; False restores sqrt + division.)
-    "cholesky_rsqrt": True,
+    # Library routines on traced fp64 input take every inverse power of a quantity from ONE reciprocal square root (the CUDA
+    # math library's 1-ulp `rsqrt`, ~12 instructions) instead of square roots and divisions (~25-50 each):
+    # `jnp.linalg.cholesky` (L_jj = s rsqrt(s), column x rsqrt(s)) and `grpy.muTT` (1/r, 1/r^2, 1/r^3 of a pair).  How a
+    # library routine forms its result is the library's choice - XLA's Cholesky expander and pygrpy make their own - so
+    # this is not covered by "reciprocal_division", which is about the user's own arithmetic.  Results move by ~1e-15;
+    # two spheres / four beads gain 4-5 % from the factor alone.  False restores sqrt + division; fp32 always uses those.
+    "library_rsqrt": True,
     # Stored trajectories: hand whole snapshot tiles (32 trajectories x 16..128 bytes per field column) to the TMA
     # unit (csrc/sde_snap_tma.cuh) whenever the output rows are 16-byte multiples.  False: the warp-transposed
     # write-out loop of csrc/sde_kernel.cuh (also the fallback for rows a tensor map cannot describe).

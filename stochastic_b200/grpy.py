@@ -14,7 +14,8 @@ import math
 
 import numpy as np
 
-from . import jnp
+from . import config, jnp
+from .trace import expr as E
 
 
 def muTT(centres, radii):
@@ -32,17 +33,29 @@ def muTT(centres, radii):
             ai, aj = float(radii[i]), float(radii[j])
             rv = [centres[i][k] - centres[j][k] for k in range(3)]
             r2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]
-            r = jnp.sqrt(r2)
-            inv_r = 1.0 / r
             s2 = ai * ai + aj * aj
-            # far field
-            pref = inv_r * (1.0 / (8 * pi))
-            far_i = pref * (1.0 + (s2 / 3.0) / r2)
-            far_r = pref * (1.0 - s2 / r2)
-            # overlapping spheres
             dm2 = (ai - aj) ** 2
-            r3 = r2 * r
-            q = 1.0 / (6 * pi * ai * aj) / (32.0 * r3)
+            if traced and E.TRACE_F64 and config.get("library_rsqrt"):
+                # fp64 kernels: every power of the distance from ONE reciprocal square root, no division (the same values
+                # within rounding; an fp64 division or square root costs ~25-50 GPU instructions, rsqrt ~12)
+                inv_r = E.unary("rsqrt", E.wrap(r2))
+                r = r2 * inv_r
+                inv_r2 = inv_r * inv_r
+                pref = inv_r * (1.0 / (8 * pi))
+                far_i = pref * (1.0 + (s2 / 3.0) * inv_r2)
+                far_r = pref * (1.0 - s2 * inv_r2)
+                r3 = r2 * r
+                q = (1.0 / (6 * pi * ai * aj) / 32.0) * (inv_r * inv_r2)
+            else:
+                r = jnp.sqrt(r2)
+                inv_r = 1.0 / r
+                # far field
+                pref = inv_r * (1.0 / (8 * pi))
+                far_i = pref * (1.0 + (s2 / 3.0) / r2)
+                far_r = pref * (1.0 - s2 / r2)
+                r3 = r2 * r
+                q = 1.0 / (6 * pi * ai * aj) / (32.0 * r3)
+            # overlapping spheres
             ov_i = q * (16.0 * r3 * (ai + aj) - (dm2 + 3.0 * r2) ** 2)
             ov_r = q * 3.0 * (dm2 - r2) ** 2
             # smaller sphere immersed in the larger one

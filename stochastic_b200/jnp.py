@@ -321,7 +321,7 @@ class _Linalg:
             s = E.wrap(a[j, j])
             for k in range(j):
                 s = s - L[j, k] * L[j, k]
-            if config.get("cholesky_rsqrt") and E.TRACE_F64:
+            if config.get("library_rsqrt") and E.TRACE_F64:
                 inv = E.unary("rsqrt", s)
                 L[j, j] = s * inv
             else:

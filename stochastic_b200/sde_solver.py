@@ -418,7 +418,7 @@ class SDESolver:
         return (self.block_size, self.min_blocks_per_sm, self.lockstep, self.snap_tile, self.warp_specialize,
                 tuple(sorted((self.ws_tuning or {}).items())), self.use_bead_kernel, self.bead_regtile,
                 config.get("warp_specialize"), config.get("reciprocal_division"), config.get("snapshot_tma"),
-                config.get("cholesky_rsqrt"))
+                config.get("library_rsqrt"))
 
     @staticmethod
     def _uses_bead_kernel(problem, force):
