@@ -124,10 +124,12 @@ def stage_count(m, p, scheme):
 
 
 def pick_block(m, p, scheme, f64, preferred=None):
-    """CTA size.  Kernels with a staged normal generator (large step bodies) use one 256-thread CTA per SM whose
-    warps are kept in lock-step by a per-step barrier; the staging area must fit in 200 KB of shared memory."""
+    """CTA size.  Kernels with a staged normal generator (large step bodies) keep their warps in lock-step by a per-step
+    barrier: 256-thread CTAs for Wagner-Platen with several noise terms, 128-thread CTAs for Euler with m > 4 (three
+    of them per SM at <= 168 registers: two spheres + 6 %, four beads + 10 % over two 256-thread CTAs at 128 registers,
+    profiles/README.md); the staging area must fit in 200 KB of shared memory."""
     stage = stage_count(m, p, scheme)
-    block = preferred or (256 if stage else 128)
+    block = preferred or (256 if stage and scheme != "euler" else 128)
     while block > 32 and stage * block * (8 if f64 else 4) > 200 * 1024:
         block //= 2
     return block

@@ -260,6 +260,8 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
         min_blocks = 2
+    if min_blocks is None and stage and block == 128 and scheme == "euler":
+        min_blocks = 3                # (see runtime.pick_block)
     if min_blocks is None and not stage and block == 128:
         # small step functions: cap the kernel at 80 registers so that six CTAs are resident per SM - the normal
         # generator is latency-bound and gains more from extra warps than from registers (two spheres +20 %, polar
