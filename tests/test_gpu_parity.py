@@ -328,6 +328,29 @@ def test_four_beads_matches_oracle_fp64():
     _assert_close(got, ref, np.float64)
 
 
+@pytest.mark.parametrize("scheme,dt,steps", [("euler", 0.05, 64), ("milstein", 0.05, 16)])
+def test_library_routines_with_and_without_reciprocal_square_roots(scheme, dt, steps):
+    """config "library_rsqrt" (the traced Cholesky and grpy.muTT from one rsqrt per pivot / pair instead of sqrt + divisions,
+    default on in fp64): both settings are the same function within rounding and both match the oracle."""
+    from stochastic_b200 import workloads
+    from oracle import problems as oprob
+    ref = osolver.solve_many(oprob.jfm_four_beads(tmax=dt * steps), scheme=scheme, dt=dt, n_trajectories=6, seed=5,
+                             chunk_size=4, dtype=np.float64)
+    out = {}
+    old = pychastic.config.get("library_rsqrt")
+    try:
+        for flag in (True, False):
+            pychastic.config.update("library_rsqrt", flag)
+            prob = workloads.four_beads(tmax=dt * steps, f64=True)
+            solver = pychastic.sde_solver.SDESolver(scheme=scheme, dt=dt)
+            out[flag] = solver.solve_many(prob, n_trajectories=6, seed=5, chunk_size=4)
+            _assert_close(out[flag], ref, np.float64)
+    finally:
+        pychastic.config.update("library_rsqrt", old)
+    a, b = np.asarray(out[True]["solution_values"]), np.asarray(out[False]["solution_values"])
+    assert 0 < np.abs(a - b).max() <= 1e-12 * np.abs(b).max()           # different instructions, same numbers
+
+
 def test_c2_wagner_platen_mid_size_with_erf_inv_tail():
     """4096 trajectories x 64 Wagner-Platen steps of BASELINE config 2 against the oracle (the small cases above draw
     ~9 k normals and reach the rare branch of erf_inv only by chance).  12 M draws here: the test first PROVES from the
