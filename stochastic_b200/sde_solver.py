@@ -330,9 +330,10 @@ def bead_ring_source(n_beads, f64, layout, block, twist=False, regtile=False):
     """Translation unit of the CTA-per-trajectory bead-chain kernel (csrc/sde_bead_kernel.cuh)."""
     return "\n".join([
         "// generated by stochastic_b200.sde_solver (bead-chain functor)",
-        f"#define SDE_NB {n_beads}", f"#define SDE_F64 {1 if f64 else 0}",
+        f"#define SDE_NB {n_beads}", f"#define SDE_F64 {1 if (f64 or regtile) else 0}",
+        f"#define SDE_BEAD_IO_F32 {1 if (regtile and not f64) else 0}",   # fp32 problem on the fp64 register-tiled kernel
         f"#define SDE_LAYOUT {1 if layout == 'partitionable' else 0}", f"#define SDE_BLOCK {block}",
-        f"#define SDE_BEAD_DMMA {1 if f64 else 0}",       # fp64: trailing update on the FP64 tensor cores
+        f"#define SDE_BEAD_DMMA {1 if (f64 or regtile) else 0}",       # fp64: trailing update on the FP64 tensor cores
         f"#define SDE_BEAD_TWIST {1 if twist else 0}",    # writhe-dependent twist energy (reference :57)
         f"#define SDE_BEAD_REGTILE {1 if regtile else 0}",  # mobility / Cholesky factor in tensor-core accumulator tiles
         f"#define SDE_BEAD_CHAIN_PER_THREAD {int(os.environ.get('SDEB200_BEAD_CHAIN_PER_THREAD', '0'))}",
@@ -413,7 +414,7 @@ class SDESolver:
         self.warp_specialize = None    # None: config "warp_specialize"; producer/consumer kernel (sde_kernel_ws.cuh)
         self.ws_tuning = None          # e.g. {"SDE_WS_PGROUPS": 2, "SDE_WS_CONSUMER_REGS": 160, ...}
         self.use_bead_kernel = False   # force the CTA-per-trajectory kernel for BeadRingProblem of any size
-        self.bead_regtile = None       # register-tiled bead kernel: None = whenever it applies (fp64, 3 N <= 128), see _bead_plan
+        self.bead_regtile = None       # register-tiled bead kernel: None = whenever it applies (3 N <= 128), see _bead_plan
 
     # -- kernel selection (shared by compile and solve_many) -----------------------------------
     def _knobs(self):
@@ -439,10 +440,11 @@ class SDESolver:
         # chain, row solves as tensor-core products): the default wherever it applies.  Measured on B200
         # (profiles/README.md, 8 880 x 100 steps): 1.07e7 against 7.3e6 trajectory-steps/s without the twist term,
         # 6.4e6 against 5.3e6 with it.
-        regtile = (f64 and 3 * nb <= 128) if self.bead_regtile is None else bool(self.bead_regtile)
+        # fp32 problems run on it too: fp32 initial condition / snapshots / random draws, fp64 in between (SDE_BEAD_IO_F32)
+        regtile = (3 * nb <= 128) if self.bead_regtile is None else bool(self.bead_regtile)
         if regtile:
-            if not (f64 and 3 * nb <= 128):
-                raise ValueError("bead_regtile needs fp64 and 3 N <= 128")
+            if not 3 * nb <= 128:
+                raise ValueError("bead_regtile needs 3 N <= 128")
             if self.block_size and self.block_size != bead_regtile_block(nb):
                 raise ValueError(f"bead_regtile: the block size is fixed by the ring size ({bead_regtile_block(nb)} threads)")
             block = bead_regtile_block(nb)

@@ -32,11 +32,12 @@ def test_bead_kernel_equals_generic_traced_kernel(dtype, tol):
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
     a = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
     solver.use_bead_kernel = True
-    for regtile in ((None, False) if f64 else (None,)):       # fp64: the register-tiled kernel (default) and the shared-memory one
+    for regtile in (None, False):       # the register-tiled kernel (default; fp32 problems: fp32 in / out, fp64 inside) and the shared-memory one
         solver.bead_regtile = regtile
         b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
-        assert f"SDE_BEAD_REGTILE {1 if f64 and regtile is None else 0}" in solver._bead_plan(
-            workloads.dna_loop(**kw), f64, "original").ks.source
+        src = solver._bead_plan(workloads.dna_loop(**kw), f64, "original").ks.source
+        assert f"SDE_BEAD_REGTILE {1 if regtile is None else 0}" in src
+        assert f"SDE_BEAD_IO_F32 {1 if regtile is None and not f64 else 0}" in src
         for k in ("time_values", "solution_values", "wiener_values"):
             x, y = np.asarray(a[k]), np.asarray(b[k])
             assert x.shape == y.shape and x.dtype == dtype
@@ -115,6 +116,29 @@ def test_strongly_overlapping_beads_match_oracle(regtile):
         assert np.abs(g - r).max() <= 1e-9 * max(np.abs(r).max(), 1e-12), (k, np.abs(g - r).max())
 
 
+@pytest.mark.parametrize("twist", [False, True])
+def test_fp32_dna_loop_on_the_register_tiled_kernel(twist):
+    """The reference's default dtype on BASELINE config C4: fp32 initial condition, snapshots, time accumulator and random
+    draws (the reference's own 32-bit stream), fp64 tensor-core arithmetic in between (SDE_BEAD_IO_F32).  Against the fp32
+    oracle and against the all-fp32 shared-memory kernel: within fp32 rounding; the Wiener path and the times bit for bit
+    ... up to the one rounding of each accumulated sum."""
+    x0 = writhed_ring(40)
+    prob = workloads.dna_loop(n_beads=40, tmax=8e-7, f64=False, twist=twist, x0=x0)
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    got = solver.solve_many(prob, n_trajectories=4, seed=1, chunk_size=2)
+    assert "SDE_BEAD_IO_F32 1" in solver._bead_plan(prob, False, "original").ks.source
+    solver.bead_regtile = False
+    smem = solver.solve_many(prob, n_trajectories=4, seed=1, chunk_size=2)
+    ref = osolver.solve_many(oprob.dna_loop(40, tmax=8e-7, twist=twist, x0=x0), scheme="euler", dt=1e-7, n_trajectories=4,
+                             seed=1, chunk_size=2, dtype=np.float32)
+    for k, tol in (("time_values", 1e-6), ("wiener_values", 2e-6), ("solution_values", 2e-5)):
+        g, r, m = np.asarray(got[k]), ref[k], np.asarray(smem[k])
+        assert g.dtype == np.float32 and g.shape == r.shape == m.shape, (k, g.dtype, g.shape)
+        scale = max(np.abs(r).max(), 1e-12)
+        assert np.abs(g - r).max() <= tol * scale, (k, "oracle", np.abs(g - r).max() / scale)
+        assert np.abs(g - m).max() <= tol * scale, (k, "shared-memory kernel", np.abs(g - m).max() / scale)
+
+
 def test_small_rings_on_the_register_tiled_kernel():
     """5 and 6 beads (2 and 3 tile rows, mostly padding) on the register-tiled kernel against the generic traced one."""
     for nb in (5, 6):
@@ -137,11 +161,13 @@ def test_twisted_ring_bead_kernel_equals_generic_traced_kernel(dtype, tol):
     solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
     a = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
     solver.use_bead_kernel = True
-    b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
-    for k in ("time_values", "solution_values", "wiener_values"):
-        x, y = np.asarray(a[k]), np.asarray(b[k])
-        assert x.shape == y.shape and x.dtype == dtype
-        assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, np.abs(x - y).max())
+    for regtile in (None, False):
+        solver.bead_regtile = regtile
+        b = solver.solve_many(workloads.dna_loop(**kw), n_trajectories=7, seed=3, chunk_size=5)
+        for k in ("time_values", "solution_values", "wiener_values"):
+            x, y = np.asarray(a[k]), np.asarray(b[k])
+            assert x.shape == y.shape and x.dtype == y.dtype == dtype
+            assert np.abs(x - y).max() <= tol * max(np.abs(x).max(), 1e-12), (k, regtile, np.abs(x - y).max())
 
 
 @pytest.mark.parametrize("twist,n_beads", [(False, 40), (True, 40), (False, 42), (True, 41), (False, 11)])
