@@ -498,3 +498,25 @@ def test_library_routines_use_reciprocal_square_roots_in_fp64_kernels():
         finally:
             pychastic.config.update("library_rsqrt", old)
         assert np.allclose(np.array(vals).reshape(5, 5), np.linalg.cholesky(C), rtol=1e-13, atol=1e-15)
+
+
+def test_bead_ring_kernel_selection_by_size_and_dtype():
+    """Which bead-chain kernel a ring gets: the register-tiled one up to 3 N = 128 in either dtype (fp32 problems with fp32
+    in / out around its fp64 arithmetic), the shared-memory one beyond or on request; small rings are traced unless forced."""
+    from stochastic_b200 import workloads
+    solver = pychastic.sde_solver.SDESolver(scheme="euler", dt=1e-7)
+    for f64 in (True, False):
+        src = solver._bead_plan(workloads.dna_loop(n_beads=40, f64=f64), f64, "original").ks.source
+        assert "#define SDE_BEAD_REGTILE 1" in src and "#define SDE_F64 1" in src and "#define SDE_BLOCK 256" in src
+        assert f"#define SDE_BEAD_IO_F32 {0 if f64 else 1}" in src
+    big = solver._bead_plan(workloads.dna_loop(n_beads=48, f64=False), False, "original").ks.source      # 3 N = 144
+    assert "#define SDE_BEAD_REGTILE 0" in big and "#define SDE_F64 0" in big and "#define SDE_BEAD_IO_F32 0" in big
+    solver.bead_regtile = False
+    off = solver._bead_plan(workloads.dna_loop(n_beads=40, f64=False), False, "original").ks.source
+    assert "#define SDE_BEAD_REGTILE 0" in off and "#define SDE_F64 0" in off
+    solver.bead_regtile = True
+    with pytest.raises(ValueError):
+        solver._bead_plan(workloads.dna_loop(n_beads=48, f64=True), True, "original")
+    assert not solver._uses_bead_kernel(workloads.dna_loop(n_beads=5, beam_length=0.125), False)
+    assert solver._uses_bead_kernel(workloads.dna_loop(n_beads=5, beam_length=0.125), True)
+    assert solver._uses_bead_kernel(workloads.dna_loop(n_beads=40), False)
