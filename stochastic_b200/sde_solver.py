@@ -256,7 +256,14 @@ def build_source(problem_a, problem_b, d, scheme, f64, layout, post=None, observ
         parts += hooks + ['#include "sde_kernel_ws.cuh"']
         return KernelSource("\n".join(parts) + "\n", m, n_obs, ws_block,
                             ring_bytes, 128)
+    user_block = block
     block = runtime.pick_block(m, p, scheme, f64, block)
+    if user_block is None and min_blocks is None and stage and scheme == "wagner_platen":
+        # Wagner-Platen outside the warp-specialised kernel (three or more noise terms): step functions of many thousand
+        # statements (rotational Brownian motion: 16 000) live in local memory at 128 registers - 128-thread CTAs at up to
+        # 255 registers run them 40 % faster (profiles/README.md)
+        if sum(1 for node in E.topo_order(outs) if node.op not in ("const", "var")) > 4000:
+            block, min_blocks = 128, 2
     if min_blocks is None and stage and block == 256:
         # measured on B200 (profiles/README.md): two 256-thread CTAs per SM at <= 128 registers beat one CTA at 244
         min_blocks = 2
